@@ -1,0 +1,133 @@
+/* rocketfft_b200 -- C ABI of the B200-native transform library (librocketfft_b200.so).
+ *
+ * Two families of entry points:
+ *
+ * (1) The ten `numba_*` symbols.  They replace, one for one and with identical
+ *     signatures, the externs the reference exports from
+ *     rocket_fft/_pocketfft_numba.cpp (good_size :25-29, c2c :31-49, dct :51-69,
+ *     dst :71-89, r2c :91-109, c2c_sym :111-143, c2r :145-163, r2r_fftpack :165-183,
+ *     r2r_separable_hartley :185-203, r2r_genuine_hartley :205-223) and that Numba-
+ *     compiled code calls by name (rocket_fft/pocketfft.py:33-128).  Arrays arrive as
+ *     pointers to Numba's array record (numba `_arraystruct.h`), see rfb200_array_record.
+ *     `data` may be a host pointer (the record of a NumPy array: the shim stages
+ *     H2D -> kernels -> D2H on the library's stream and returns when the result is in
+ *     host memory) or a device pointer (detected with cudaPointerGetAttributes: no
+ *     staging, the call is asynchronous on the current library stream).
+ *     As in the reference they return void; failures are recorded and can be read
+ *     with rfb200_last_error().
+ *
+ * (2) `rfb200_*` device entry points for arrays that are already resident in HBM
+ *     (`__cuda_array_interface__`): plain shape / byte-stride / axes arrays, raw device
+ *     pointers and a CUDA stream.  They return 0 on success, nonzero on error.
+ *
+ * There is no CPU fallback behind any of these: every transform runs as sm_100a CUDA
+ * kernels; only good_size is host integer arithmetic.
+ */
+#ifndef ROCKETFFT_B200_H
+#define ROCKETFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Numba's array record (numba/_arraystruct.h), as read by the reference at
+ * _pocketfft_numba.cpp:34-37: shape = shape_and_strides[0..ndim),
+ * strides (bytes, signed) = shape_and_strides[ndim..2*ndim). */
+typedef struct rfb200_array_record {
+    void *meminfo;
+    void *parent;
+    intptr_t nitems;
+    intptr_t itemsize;
+    void *data;
+    intptr_t shape_and_strides[1]; /* really 2*ndim entries */
+} rfb200_array_record;
+
+/* ---- (1) drop-in symbols (reference: _pocketfft_numba.cpp:25-223) ------------- */
+uint64_t numba_good_size(uint64_t target, bool real);
+void numba_c2c(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+               rfb200_array_record *axes, bool forward, double fct, uint64_t nthreads);
+void numba_r2c(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+               rfb200_array_record *axes, bool forward, double fct, uint64_t nthreads);
+void numba_c2r(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+               rfb200_array_record *axes, bool forward, double fct, uint64_t nthreads);
+void numba_c2c_sym(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                   rfb200_array_record *axes, bool forward, double fct, uint64_t nthreads);
+void numba_dct(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+               rfb200_array_record *axes, uint64_t type, double fct, bool ortho, uint64_t nthreads);
+void numba_dst(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+               rfb200_array_record *axes, uint64_t type, double fct, bool ortho, uint64_t nthreads);
+void numba_r2r_fftpack(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                       rfb200_array_record *axes, bool real2hermitian, bool forward, double fct,
+                       uint64_t nthreads);
+void numba_r2r_separable_hartley(uint64_t ndim, const rfb200_array_record *ain,
+                                 rfb200_array_record *aout, rfb200_array_record *axes, double fct,
+                                 uint64_t nthreads);
+void numba_r2r_genuine_hartley(uint64_t ndim, const rfb200_array_record *ain,
+                               rfb200_array_record *aout, rfb200_array_record *axes, double fct,
+                               uint64_t nthreads);
+
+/* ---- (2) device-resident entry points ------------------------------------------- */
+/* precision: 0 = single (float32 / complex64), 1 = double (float64 / complex128).
+ * `shape` is the shape the reference reads: the input's for every op except c2r,
+ * where it is the (real) output's.  Strides are signed bytes.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream). */
+typedef enum { RFB200_F32 = 0, RFB200_F64 = 1 } rfb200_precision;
+
+int rfb200_c2c(int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+               const int64_t *stride_out, size_t naxes, const uint64_t *axes, int forward,
+               double fct, const void *d_in, void *d_out, void *stream);
+int rfb200_r2c(int precision, size_t ndim, const int64_t *shape_in, const int64_t *stride_in,
+               const int64_t *stride_out, size_t naxes, const uint64_t *axes, int forward,
+               double fct, const void *d_in, void *d_out, void *stream);
+int rfb200_c2r(int precision, size_t ndim, const int64_t *shape_out, const int64_t *stride_in,
+               const int64_t *stride_out, size_t naxes, const uint64_t *axes, int forward,
+               double fct, const void *d_in, void *d_out, void *stream);
+int rfb200_c2c_sym(int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+                   const int64_t *stride_out, size_t naxes, const uint64_t *axes, int forward,
+                   double fct, const void *d_in, void *d_out, void *stream);
+int rfb200_dct(int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+               const int64_t *stride_out, size_t naxes, const uint64_t *axes, int type,
+               double fct, int ortho, const void *d_in, void *d_out, void *stream);
+int rfb200_dst(int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+               const int64_t *stride_out, size_t naxes, const uint64_t *axes, int type,
+               double fct, int ortho, const void *d_in, void *d_out, void *stream);
+int rfb200_r2r_fftpack(int precision, size_t ndim, const int64_t *shape,
+                       const int64_t *stride_in, const int64_t *stride_out, size_t naxes,
+                       const uint64_t *axes, int real2hermitian, int forward, double fct,
+                       const void *d_in, void *d_out, void *stream);
+int rfb200_r2r_separable_hartley(int precision, size_t ndim, const int64_t *shape,
+                                 const int64_t *stride_in, const int64_t *stride_out,
+                                 size_t naxes, const uint64_t *axes, double fct,
+                                 const void *d_in, void *d_out, void *stream);
+int rfb200_r2r_genuine_hartley(int precision, size_t ndim, const int64_t *shape,
+                               const int64_t *stride_in, const int64_t *stride_out,
+                               size_t naxes, const uint64_t *axes, double fct, const void *d_in,
+                               void *d_out, void *stream);
+
+/* ---- housekeeping ----------------------------------------------------------------- */
+/* Last error message of the calling thread ("" if none); cleared by rfb200_clear_error. */
+const char *rfb200_last_error(void);
+void rfb200_clear_error(void);
+/* Drop all cached plans (device twiddle/chirp tables) of the current device. */
+void rfb200_plan_cache_clear(void);
+/* Stream used by the numba_* shims for the calling thread (cudaStream_t as void*; NULL is
+ * the legacy default stream).  Default: a library-owned non-blocking stream per device,
+ * restored by rfb200_use_library_stream(). */
+void rfb200_set_stream(void *stream);
+void rfb200_use_library_stream(void);
+/* Number of kernel launches issued by this library since the last reset (all threads). */
+uint64_t rfb200_launch_count(void);
+void rfb200_launch_count_reset(void);
+/* DST-II/III with ortho=true: 1 (default) reproduces the reference, which scales element
+ * 0 (H:3033-3039, README.md:61-65); 0 scales element N-1 as SciPy does. */
+void rfb200_set_dst_ortho_quirk(int enabled);
+/* Library version string. */
+const char *rfb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROCKETFFT_B200_H */

@@ -1,0 +1,29 @@
+"""rocket_fft_b200 -- B200-native (sm_100a) transform engine behind rocket-fft's
+low-level API.  See lowlevel.py for the interface and DESIGN.md for the design."""
+from .lowlevel import (  # noqa: F401
+    LIB_PATH,
+    TransformError,
+    c2c,
+    c2c_sym,
+    c2r,
+    dct,
+    dst,
+    fftpack,
+    genuine_hartley,
+    good_size,
+    last_error,
+    launch_count,
+    launch_count_reset,
+    lib,
+    plan_cache_clear,
+    r2c,
+    r2r_fftpack,
+    r2r_genuine_hartley,
+    r2r_separable_hartley,
+    separable_hartley,
+    set_dst_ortho_quirk,
+    set_stream,
+    version,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,280 @@
+// C ABI of librocketfft_b200.so: the ten numba_* drop-in symbols and the rfb200_* device entry
+// points declared in include/rocketfft_b200.h.
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "../../include/rocketfft_b200.h"
+#include "engine.h"
+
+using namespace rfb;
+
+#define RFB_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+// ---- library stream (per device) ----------------------------------------------------------
+std::mutex g_stream_mu;
+cudaStream_t g_lib_stream[64] = {nullptr};
+thread_local bool g_user_stream_set = false;
+thread_local cudaStream_t g_user_stream = nullptr;
+
+cudaStream_t lib_stream() {
+    if (g_user_stream_set) return g_user_stream;
+    int dev = 0;
+    RFB_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    if (!g_lib_stream[dev & 63]) RFB_CUDA_CHECK(cudaStreamCreateWithFlags(&g_lib_stream[dev & 63], cudaStreamNonBlocking));
+    return g_lib_stream[dev & 63];
+}
+
+enum OpKind { OP_C2C, OP_R2C, OP_C2R, OP_C2C_SYM, OP_DCT, OP_DST, OP_FFTPACK, OP_SEP_HARTLEY, OP_GEN_HARTLEY };
+
+struct OpFlags {
+    bool forward = true, ortho = false, r2h = false;
+    int type = 2;
+};
+
+bool in_is_complex(OpKind k) { return k == OP_C2C || k == OP_C2R; }
+bool out_is_complex(OpKind k) { return k == OP_C2C || k == OP_R2C || k == OP_C2C_SYM; }
+
+void dispatch(OpKind k, const NdArgs &a, const OpFlags &f, cudaStream_t s) {
+    for (auto ax : a.axes)
+        if (ax >= a.shape.size()) { set_error("axis out of range"); throw Error(); }
+    switch (k) {
+        case OP_C2C: op_c2c(a, f.forward, s); break;
+        case OP_R2C: op_r2c(a, f.forward, s); break;
+        case OP_C2R: op_c2r(a, f.forward, s); break;
+        case OP_C2C_SYM: op_c2c_sym(a, f.forward, s); break;
+        case OP_DCT: op_dcst(a, f.type, f.ortho, true, s); break;
+        case OP_DST: op_dcst(a, f.type, f.ortho, false, s); break;
+        case OP_FFTPACK: op_fftpack(a, f.r2h, f.forward, s); break;
+        case OP_SEP_HARTLEY: op_separable_hartley(a, s); break;
+        case OP_GEN_HARTLEY: op_genuine_hartley(a, s); break;
+    }
+}
+
+// byte span [lo, hi) covered by an array relative to its data pointer
+void span_of(const std::vector<int64_t> &shape, const std::vector<int64_t> &st, int64_t itemsize, int64_t &lo, int64_t &hi) {
+    lo = 0;
+    hi = 0;
+    for (size_t d = 0; d < shape.size(); ++d) {
+        const int64_t ext = (shape[d] - 1) * st[d];
+        if (ext < 0) lo += ext; else hi += ext;
+    }
+    hi += itemsize;
+}
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t s;
+    DevBuf(size_t n, cudaStream_t st) : s(st) { RFB_CUDA_CHECK(cudaMallocAsync(&p, n ? n : 16, st)); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+// The numba_* path: arrays described by Numba array records; host data is staged.
+void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                   const rfb200_array_record *axes, double fct, const OpFlags &f) {
+    clear_error();
+    try {
+        NdArgs a;
+        const rfb200_array_record *shp_src = (k == OP_C2R) ? aout : ain;
+        a.shape.assign(shp_src->shape_and_strides, shp_src->shape_and_strides + ndim);
+        a.sin.assign(ain->shape_and_strides + ndim, ain->shape_and_strides + 2 * ndim);
+        a.sout.assign(aout->shape_and_strides + ndim, aout->shape_and_strides + 2 * ndim);
+        const uint64_t *ax = reinterpret_cast<const uint64_t *>(axes->data);
+        a.axes.assign(ax, ax + axes->nitems);
+        a.fct = fct;
+        for (auto s : a.shape)
+            if (s == 0) return;
+        if (a.axes.empty()) return;
+        // precision from the input's item size (reference: _pocketfft_numba.cpp:38, 58, 98, 152)
+        const int64_t isz = ain->itemsize;
+        const int64_t in_scalar = in_is_complex(k) ? isz / 2 : isz;
+        a.prec = (in_scalar == 8) ? 1 : 0;
+        const int64_t ssz = a.prec ? 8 : 4;
+        const int64_t in_item = in_is_complex(k) ? 2 * ssz : ssz;
+        const int64_t out_item = out_is_complex(k) ? 2 * ssz : ssz;
+        const size_t L = (size_t)a.axes.back();
+        std::vector<int64_t> shape_in = a.shape, shape_out = a.shape;
+        if (k == OP_R2C) shape_out[L] = a.shape[L] / 2 + 1;
+        if (k == OP_C2R) shape_in[L] = a.shape[L] / 2 + 1;
+
+        cudaStream_t s = lib_stream();
+        const bool dev_in = is_device_ptr(ain->data), dev_out = is_device_ptr(aout->data);
+        if (dev_in != dev_out) { set_error("input and output must both be host or both be device arrays"); throw Error(); }
+        if (dev_in) {
+            a.in = (const char *)ain->data;
+            a.out = (char *)aout->data;
+            dispatch(k, a, f, s);
+            return;
+        }
+        // ---- host arrays: H2D -> kernels -> D2H, synchronous for the caller ----
+        int64_t ilo, ihi, olo, ohi;
+        span_of(shape_in, a.sin, in_item, ilo, ihi);
+        span_of(shape_out, a.sout, out_item, olo, ohi);
+        const char *hin = (const char *)ain->data + ilo;
+        char *hout = (char *)aout->data + olo;
+        const size_t ibytes = (size_t)(ihi - ilo), obytes = (size_t)(ohi - olo);
+        const bool same = (hin == hout) && (ibytes == obytes);
+        DevBuf din(ibytes, s);
+        RFB_CUDA_CHECK(cudaMemcpyAsync(din.p, hin, ibytes, cudaMemcpyHostToDevice, s));
+        DevBuf *dout_own = nullptr;
+        struct G { DevBuf *&p; ~G() { delete p; } } g{dout_own};
+        char *dout_base;
+        if (same) dout_base = (char *)din.p;
+        else {
+            dout_own = new DevBuf(obytes, s);
+            dout_base = (char *)dout_own->p;
+            uint64_t dense = (uint64_t)out_item;
+            for (auto v : shape_out) dense *= (uint64_t)v;
+            if (dense != obytes)  // gaps between elements must survive the round trip
+                RFB_CUDA_CHECK(cudaMemcpyAsync(dout_base, hout, obytes, cudaMemcpyHostToDevice, s));
+        }
+        a.in = (const char *)din.p - ilo;
+        a.out = dout_base - olo;
+        dispatch(k, a, f, s);
+        RFB_CUDA_CHECK(cudaMemcpyAsync(hout, dout_base, obytes, cudaMemcpyDeviceToHost, s));
+        RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+    } catch (const Error &) {
+        fprintf(stderr, "rocketfft_b200: %s\n", last_error());
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        fprintf(stderr, "rocketfft_b200: %s\n", e.what());
+    }
+}
+
+int run_device_op(OpKind k, int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+                  const int64_t *stride_out, size_t naxes, const uint64_t *axes, double fct, const void *d_in,
+                  void *d_out, void *stream, const OpFlags &f) {
+    clear_error();
+    try {
+        NdArgs a;
+        a.prec = precision ? 1 : 0;
+        a.shape.assign(shape, shape + ndim);
+        a.sin.assign(stride_in, stride_in + ndim);
+        a.sout.assign(stride_out, stride_out + ndim);
+        a.axes.assign(axes, axes + naxes);
+        a.in = (const char *)d_in;
+        a.out = (char *)d_out;
+        a.fct = fct;
+        dispatch(k, a, f, (cudaStream_t)stream);
+        return 0;
+    } catch (const Error &) {
+        return 1;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return 1;
+    }
+}
+
+OpFlags mk_flags(bool forward, int type = 2, bool ortho = false, bool r2h = false) {
+    OpFlags f;
+    f.forward = forward;
+    f.type = type;
+    f.ortho = ortho;
+    f.r2h = r2h;
+    return f;
+}
+
+}  // namespace
+
+// ---- (1) numba_* -------------------------------------------------------------------------------
+RFB_EXPORT uint64_t numba_good_size(uint64_t target, bool real) { return rfb::good_size(target, real); }
+
+RFB_EXPORT void numba_c2c(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                          rfb200_array_record *axes, bool forward, double fct, uint64_t) {
+    run_record_op(OP_C2C, ndim, ain, aout, axes, fct, mk_flags(forward));
+}
+RFB_EXPORT void numba_r2c(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                          rfb200_array_record *axes, bool forward, double fct, uint64_t) {
+    run_record_op(OP_R2C, ndim, ain, aout, axes, fct, mk_flags(forward));
+}
+RFB_EXPORT void numba_c2r(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                          rfb200_array_record *axes, bool forward, double fct, uint64_t) {
+    run_record_op(OP_C2R, ndim, ain, aout, axes, fct, mk_flags(forward));
+}
+RFB_EXPORT void numba_c2c_sym(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                              rfb200_array_record *axes, bool forward, double fct, uint64_t) {
+    run_record_op(OP_C2C_SYM, ndim, ain, aout, axes, fct, mk_flags(forward));
+}
+RFB_EXPORT void numba_dct(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                          rfb200_array_record *axes, uint64_t type, double fct, bool ortho, uint64_t) {
+    run_record_op(OP_DCT, ndim, ain, aout, axes, fct, mk_flags(true, (int)type, ortho));
+}
+RFB_EXPORT void numba_dst(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                          rfb200_array_record *axes, uint64_t type, double fct, bool ortho, uint64_t) {
+    run_record_op(OP_DST, ndim, ain, aout, axes, fct, mk_flags(true, (int)type, ortho));
+}
+RFB_EXPORT void numba_r2r_fftpack(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                                  rfb200_array_record *axes, bool real2hermitian, bool forward, double fct, uint64_t) {
+    run_record_op(OP_FFTPACK, ndim, ain, aout, axes, fct, mk_flags(forward, 2, false, real2hermitian));
+}
+RFB_EXPORT void numba_r2r_separable_hartley(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                                            rfb200_array_record *axes, double fct, uint64_t) {
+    run_record_op(OP_SEP_HARTLEY, ndim, ain, aout, axes, fct, mk_flags(true));
+}
+RFB_EXPORT void numba_r2r_genuine_hartley(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                                          rfb200_array_record *axes, double fct, uint64_t) {
+    run_record_op(OP_GEN_HARTLEY, ndim, ain, aout, axes, fct, mk_flags(true));
+}
+
+// ---- (2) rfb200_* --------------------------------------------------------------------------------
+#define DEV_ARGS                                                                                               \
+    int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in, const int64_t *stride_out,    \
+        size_t naxes, const uint64_t *axes
+#define DEV_PASS precision, ndim, shape, stride_in, stride_out, naxes, axes
+
+RFB_EXPORT int rfb200_c2c(DEV_ARGS, int forward, double fct, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_C2C, DEV_PASS, fct, d_in, d_out, stream, mk_flags(forward != 0));
+}
+RFB_EXPORT int rfb200_r2c(DEV_ARGS, int forward, double fct, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_R2C, DEV_PASS, fct, d_in, d_out, stream, mk_flags(forward != 0));
+}
+RFB_EXPORT int rfb200_c2r(DEV_ARGS, int forward, double fct, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_C2R, DEV_PASS, fct, d_in, d_out, stream, mk_flags(forward != 0));
+}
+RFB_EXPORT int rfb200_c2c_sym(DEV_ARGS, int forward, double fct, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_C2C_SYM, DEV_PASS, fct, d_in, d_out, stream, mk_flags(forward != 0));
+}
+RFB_EXPORT int rfb200_dct(DEV_ARGS, int type, double fct, int ortho, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_DCT, DEV_PASS, fct, d_in, d_out, stream, mk_flags(true, type, ortho != 0));
+}
+RFB_EXPORT int rfb200_dst(DEV_ARGS, int type, double fct, int ortho, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_DST, DEV_PASS, fct, d_in, d_out, stream, mk_flags(true, type, ortho != 0));
+}
+RFB_EXPORT int rfb200_r2r_fftpack(DEV_ARGS, int real2hermitian, int forward, double fct, const void *d_in,
+                                  void *d_out, void *stream) {
+    return run_device_op(OP_FFTPACK, DEV_PASS, fct, d_in, d_out, stream, mk_flags(forward != 0, 2, false, real2hermitian != 0));
+}
+RFB_EXPORT int rfb200_r2r_separable_hartley(DEV_ARGS, double fct, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_SEP_HARTLEY, DEV_PASS, fct, d_in, d_out, stream, mk_flags(true));
+}
+RFB_EXPORT int rfb200_r2r_genuine_hartley(DEV_ARGS, double fct, const void *d_in, void *d_out, void *stream) {
+    return run_device_op(OP_GEN_HARTLEY, DEV_PASS, fct, d_in, d_out, stream, mk_flags(true));
+}
+
+// ---- housekeeping ---------------------------------------------------------------------------------
+RFB_EXPORT const char *rfb200_last_error(void) { return rfb::last_error(); }
+RFB_EXPORT void rfb200_clear_error(void) { rfb::clear_error(); }
+RFB_EXPORT void rfb200_plan_cache_clear(void) { rfb::plan_cache_clear(); }
+RFB_EXPORT void rfb200_set_stream(void *stream) {
+    g_user_stream_set = true;
+    g_user_stream = (cudaStream_t)stream;
+}
+RFB_EXPORT void rfb200_use_library_stream(void) { g_user_stream_set = false; }
+RFB_EXPORT uint64_t rfb200_launch_count(void) { return rfb::launch_count(); }
+RFB_EXPORT void rfb200_launch_count_reset(void) { rfb::launch_count_reset(); }
+RFB_EXPORT void rfb200_set_dst_ortho_quirk(int enabled) { rfb::set_dst_ortho_quirk(enabled != 0); }
+RFB_EXPORT const char *rfb200_version(void) { return "rocketfft_b200 0.1.0 (sm_100a)"; }

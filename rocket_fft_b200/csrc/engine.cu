@@ -1,0 +1,630 @@
+// Line engine: batched 1-D complex DFTs over arbitrarily strided memory.
+//   * lines that fit in shared memory      -> one fused tile kernel (tile_kernel.cuh)
+//   * long smooth lines, n = n1*n2          -> "four-step": two tile-kernel launches with the
+//                                             n1 x n2 twiddle fused into the first and the
+//                                             transposition folded into the second's addressing
+//   * lines with a prime factor > 64        -> Bluestein chirp-z on a power-of-two length
+// (Counterpart of general_nd / pocketfft_c / fftblue in the reference,
+//  _pocketfft_hdronly.h:3568-3607, 2834-2912, 2723-2828 -- different algorithms, new code.)
+#include "engine.h"
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tile_kernel.cuh"
+
+namespace rfb {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(); }
+void launch_count_reset() { g_launches.store(0); }
+void count_launch() { g_launches.fetch_add(1); }
+
+#define RFB_AFTER_LAUNCH()                      \
+    do {                                        \
+        g_launches.fetch_add(1);                \
+        RFB_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
+
+static const size_t MAX_SMEM = 227 * 1024;
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// ---------------------------------------------------------------------------------------
+// scratch
+// ---------------------------------------------------------------------------------------
+static void init_pool_once() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && !done[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        done[dev] = true;
+    }
+}
+
+Scratch::Scratch(size_t bytes, cudaStream_t st) : s(st) {
+    init_pool_once();
+    RFB_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, st));
+}
+Scratch::~Scratch() {
+    if (p) cudaFreeAsync(p, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------
+static inline int64_t iabs64(int64_t v) { return v < 0 ? -v : v; }
+
+struct BatchIdx {
+    int nd;
+    uint32_t ext[8];
+    FastDiv d[8];
+    int64_t is[8], os[8];
+};
+
+static uint64_t total_lines(const std::vector<Dim> &b) {
+    uint64_t L = 1;
+    for (auto &d : b) L *= (uint64_t)d.n;
+    return L;
+}
+
+static BatchIdx make_batch_idx(const std::vector<Dim> &b) {
+    BatchIdx bi;
+    if (b.size() > 8) { set_error("more than 9 array dimensions are not supported"); throw Error(); }
+    bi.nd = (int)b.size();
+    for (int i = 0; i < bi.nd; ++i) {
+        bi.ext[i] = (uint32_t)b[i].n;
+        bi.d[i] = make_fastdiv((uint32_t)b[i].n);
+        bi.is[i] = b[i].is;
+        bi.os[i] = b[i].os;
+    }
+    return bi;
+}
+
+__device__ __forceinline__ void batch_offsets(const BatchIdx &bi, uint32_t l, int64_t &oi, int64_t &oo) {
+    oi = 0; oo = 0;
+    for (int d = 0; d < bi.nd; ++d) {
+        uint32_t q, r;
+        fdivmod(l, bi.d[d], q, r);
+        oi += (int64_t)r * bi.is[d];
+        oo += (int64_t)r * bi.os[d];
+        l = q;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// gather / scatter kernels for lines that go through scratch (long lines with a fused mode)
+// grid: x over elements of a line, y over lines (grid-stride)
+// ---------------------------------------------------------------------------------------
+template <typename T, bool ALIGNED>
+__global__ void gather_lines_kernel(BatchIdx bi, uint32_t L, const char *in, int64_t sa, cx<T> *scratch, uint32_t n,
+                                    uint32_t n_in, int mode, int flags) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    for (uint32_t l = blockIdx.y; l < L; l += gridDim.y) {
+        int64_t oi, oo;
+        batch_offsets(bi, l, oi, oo);
+        scratch[(size_t)l * n + e] = load_value<T, ALIGNED>(mode, flags, in + oi, sa, e, n, n_in);
+    }
+}
+
+template <typename T, bool ALIGNED>
+__global__ void scatter_lines_kernel(BatchIdx bi, uint32_t L, const cx<T> *scratch, char *out, int64_t sa, uint32_t n,
+                                     uint32_t n_out, int mode, int flags) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    for (uint32_t l = blockIdx.y; l < L; l += gridDim.y) {
+        int64_t oi, oo;
+        batch_offsets(bi, l, oi, oo);
+        const cx<T> v = scratch[(size_t)l * n + store_bin(mode, j)];
+        store_value<T, ALIGNED>(mode, flags, out + oo, sa, j, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Bluestein kernels
+// ---------------------------------------------------------------------------------------
+// a[l][m] = x[l][m] * chirp[m] (m < n), 0 (n <= m < M); backward handled by the swap identity
+template <typename T, bool ALIGNED>
+__global__ void blue_pre_kernel(BatchIdx bi, uint32_t L, const char *in, int64_t sa, cx<T> *a, uint32_t n, uint32_t M,
+                                const cx<T> *__restrict__ chirp, int backward) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    for (uint32_t l = blockIdx.y; l < L; l += gridDim.y) {
+        cx<T> v = mk<T>(T(0), T(0));
+        if (m < n) {
+            int64_t oi, oo;
+            batch_offsets(bi, l, oi, oo);
+            v = ld_cx<T, ALIGNED>(in + oi + (int64_t)m * sa);
+            if (backward) v = cswap(v);
+            v = cmul(v, chirp[m]);
+        }
+        a[(size_t)l * M + m] = v;
+    }
+}
+
+template <typename T>
+__global__ void blue_mul_kernel(cx<T> *a, uint32_t L, uint32_t M, const cx<T> *__restrict__ bhat) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const cx<T> b = bhat[m];
+    for (uint32_t l = blockIdx.y; l < L; l += gridDim.y) a[(size_t)l * M + m] = cmul(a[(size_t)l * M + m], b);
+}
+
+template <typename T, bool ALIGNED>
+__global__ void blue_post_kernel(BatchIdx bi, uint32_t L, const cx<T> *y, char *out, int64_t sa, uint32_t n, uint32_t M,
+                                 const cx<T> *__restrict__ chirp, T fct, int backward) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cx<T> w = chirp[k];
+    for (uint32_t l = blockIdx.y; l < L; l += gridDim.y) {
+        int64_t oi, oo;
+        batch_offsets(bi, l, oi, oo);
+        cx<T> v = cscale(cmul(y[(size_t)l * M + k], w), fct);
+        if (backward) v = cswap(v);
+        st_cx<T, ALIGNED>(out + oo + (int64_t)k * sa, v);
+    }
+}
+
+// b[m] = conj(chirp[|m|]) / M wrapped onto length M
+template <typename T>
+__global__ void blue_kernel_seq(cx<T> *b, uint32_t n, uint32_t M, const cx<T> *__restrict__ chirp) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    cx<T> v = mk<T>(T(0), T(0));
+    const T inv = T(1) / T(M);
+    if (m < n) v = mk<T>(chirp[m].x * inv, -chirp[m].y * inv);
+    else if (M - m < n) v = mk<T>(chirp[M - m].x * inv, -chirp[M - m].y * inv);
+    b[m] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// tile launch
+// ---------------------------------------------------------------------------------------
+struct TilePlan {
+    std::vector<uint32_t> sched;
+    uint32_t pitch, padsh, W, threads;
+    size_t smem;
+    bool load_lf, store_lf;
+};
+
+static bool alignment_ok(const LineJob &job, const std::vector<Dim> &dims) {
+    const int64_t esz = job.prec ? 16 : 8;
+    auto ok = [&](int64_t v) { return (v % esz) == 0; };
+    bool cin = (job.load_mode == LD_C2C || job.load_mode == LD_HERM);
+    bool cout = (job.store_mode == ST_C2C || job.store_mode == ST_HALF);
+    bool a = true;
+    if (cin) {
+        a = a && ok((int64_t)(uintptr_t)job.in) && ok(job.is);
+        for (auto &d : dims) a = a && ok(d.is);
+    }
+    if (cout) {
+        a = a && ok((int64_t)(uintptr_t)job.out) && ok(job.os);
+        for (auto &d : dims) a = a && ok(d.os);
+    }
+    return a;
+}
+
+// Decide the tile shape for lines of length n; false if a line does not fit.
+static bool plan_tile(const LineJob &job, const std::vector<Dim> &dims, TilePlan &tp) {
+    const uint64_t n = job.n;
+    const size_t esz = job.prec ? 16 : 8;
+    if (n > (1u << 20)) return false;
+    if (n == 1) tp.sched.clear();
+    else {
+        tp.sched = radix_schedule(n, RMAX_GENERIC);
+        if (tp.sched.empty() || tp.sched.size() > (size_t)MAXP) return false;
+    }
+    tp.padsh = (uint32_t)env_int("RFB200_PADSH", job.prec ? 4 : 5);
+    uint32_t pitch = (uint32_t)((n - 1) + ((n - 1) >> tp.padsh) + 1);
+    pitch |= 1u;
+    tp.pitch = pitch;
+    const size_t line_bytes = (size_t)pitch * esz;
+    if (line_bytes > MAX_SMEM) return false;
+    const uint64_t e0 = dims.empty() ? 1 : (uint64_t)dims[0].n;
+    tp.load_lf = !dims.empty() && iabs64(dims[0].is) < iabs64(job.is);
+    tp.store_lf = !dims.empty() && iabs64(dims[0].os) < iabs64(job.os);
+    const uint64_t wfit = MAX_SMEM / line_bytes;
+    uint64_t W;
+    if (tp.load_lf || tp.store_lf) {
+        // neighbouring lines are adjacent in memory: take enough of them for 128-byte rows,
+        // more when lines are short
+        uint64_t wpref = 128 / esz;
+        const size_t budget = 64 * 1024;
+        while (wpref * 2 * line_bytes <= budget && wpref < 64) wpref *= 2;
+        W = std::min<uint64_t>(wpref, wfit);
+    } else {
+        const size_t budget = 32 * 1024;  // several CTAs per SM for short lines
+        W = std::max<uint64_t>(1, budget / line_bytes);
+        W = std::min<uint64_t>(W, wfit);
+        W = std::min<uint64_t>(W, 256);
+    }
+    W = std::max<uint64_t>(1, std::min<uint64_t>(W, e0));
+    tp.W = (uint32_t)W;
+    tp.smem = (size_t)W * line_bytes;
+    uint64_t work = W * n;
+    uint32_t th = (uint32_t)std::min<uint64_t>(512, std::max<uint64_t>(64, ((work / 4 + 31) / 32) * 32));
+    tp.threads = th;
+    return true;
+}
+
+template <typename T, bool ALIGNED>
+static void launch_tile_typed(const LineJob &job, const std::vector<Dim> &dims, const TilePlan &tp, cudaStream_t s) {
+    TileGeom<T> g;
+    memset(&g, 0, sizeof(g));
+    const uint32_t n = (uint32_t)job.n;
+    g.n = n;
+    g.npass = (uint32_t)tp.sched.size();
+    uint32_t l1 = 1;
+    for (uint32_t i = 0; i < g.npass; ++i) {
+        PassInfo &ps = g.pass[i];
+        ps.R = tp.sched[i];
+        ps.l1 = l1;
+        ps.ido = n / (l1 * ps.R);
+        ps.d_ido = make_fastdiv(ps.ido);
+        ps.d_nbl = make_fastdiv(n / ps.R);
+        ps.d_R = make_fastdiv(ps.R);
+        l1 *= ps.R;
+    }
+    g.W = tp.W;
+    g.pitch = tp.pitch;
+    g.padsh = tp.padsh;
+    g.d_n = make_fastdiv(n);
+    g.d_W = make_fastdiv(tp.W);
+    g.load_line_fast = tp.load_lf ? 1 : 0;
+    g.store_line_fast = tp.store_lf ? 1 : 0;
+    g.load_mode = job.load_mode;
+    g.store_mode = job.store_mode;
+    g.flags = job.flags;
+    g.n_in = (uint32_t)(job.n_in ? job.n_in : job.n);
+    g.n_out = (job.store_mode == ST_HALF) ? n / 2 + 1 : n;
+    g.d_nout = make_fastdiv(g.n_out);
+    g.backward = job.backward ? 1 : 0;
+    g.in_sa = job.is;
+    g.out_sa = job.os;
+    g.tw_dim = -1;
+    for (int d = 0; d < MAXB; ++d) {
+        if (d < (int)dims.size()) {
+            g.bext[d] = (uint32_t)dims[d].n;
+            g.in_bs[d] = dims[d].is;
+            g.out_bs[d] = dims[d].os;
+            if (dims[d].tw && job.twN) g.tw_dim = d;
+        } else {
+            g.bext[d] = 1;
+            g.in_bs[d] = 0;
+            g.out_bs[d] = 0;
+        }
+    }
+    const uint32_t tiles0 = (g.bext[0] + tp.W - 1) / tp.W;
+    g.d_t0 = make_fastdiv(tiles0);
+    g.d_e1 = make_fastdiv(g.bext[1]);
+    const uint64_t ntiles = (uint64_t)tiles0 * g.bext[1] * g.bext[2];
+    if (ntiles >= (1ull << 31)) { set_error("too many tiles in one launch"); throw Error(); }
+    g.in = job.in;
+    g.out = job.out;
+    g.tw = (n > 1) ? (const cx<T> *)get_table(TAB_LINE, job.prec, n, 0) : nullptr;
+    g.fct = (T)job.fct;
+    if (g.tw_dim >= 0) {
+        const uint32_t S = split_size(job.twN);
+        g.d_twS = make_fastdiv(S);
+        g.twA = (const cx<T> *)get_table(TAB_SPLIT_A, job.prec, job.twN, S);
+        g.twB = (const cx<T> *)get_table(TAB_SPLIT_B, job.prec, job.twN, S);
+    }
+    auto kern = fft_tile_kernel<T, ALIGNED>;
+    static thread_local int dev_set = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_set != dev) {
+        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_SMEM));
+        dev_set = dev;
+    }
+    kern<<<(unsigned)ntiles, tp.threads, tp.smem, s>>>(g);
+    RFB_AFTER_LAUNCH();
+}
+
+static void launch_tile(const LineJob &job, const std::vector<Dim> &dims, const TilePlan &tp, cudaStream_t s) {
+    // more batch dims than one launch takes: peel the outermost ones on the host
+    if (dims.size() > (size_t)MAXB) {
+        std::vector<Dim> inner(dims.begin(), dims.end() - 1);
+        const Dim &o = dims.back();
+        if (o.tw && job.twN) { set_error("internal: four-step dim peeled"); throw Error(); }
+        for (int64_t i = 0; i < o.n; ++i) {
+            LineJob sub = job;
+            sub.in = job.in + i * o.is;
+            sub.out = job.out + i * o.os;
+            launch_tile(sub, inner, tp, s);
+        }
+        return;
+    }
+    const bool al = alignment_ok(job, dims);
+    if (job.prec) {
+        if (al) launch_tile_typed<double, true>(job, dims, tp, s);
+        else launch_tile_typed<double, false>(job, dims, tp, s);
+    } else {
+        if (al) launch_tile_typed<float, true>(job, dims, tp, s);
+        else launch_tile_typed<float, false>(job, dims, tp, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// elementwise launch helpers
+// ---------------------------------------------------------------------------------------
+static dim3 ew_grid(uint64_t n_e, uint64_t L) {
+    return dim3((unsigned)((n_e + 255) / 256), (unsigned)std::min<uint64_t>(L, 32768), 1);
+}
+
+static std::vector<Dim> contiguous_batch(const std::vector<Dim> &b, uint64_t line_bytes, bool as_input) {
+    // same extents, C-order contiguous strides on the scratch side
+    std::vector<Dim> r = b;
+    int64_t acc = (int64_t)line_bytes;
+    for (size_t i = 0; i < r.size(); ++i) {  // dim 0 fastest in BatchIdx order
+        if (as_input) r[i].is = acc; else r[i].os = acc;
+        acc *= r[i].n;
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// the three algorithms
+// ---------------------------------------------------------------------------------------
+static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+static void run_via_scratch(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+
+static bool choose_split(uint64_t n, int prec, uint64_t &n1, uint64_t &n2) {
+    // divisor pair closest to sqrt(n) whose members both factor into radices <= RMAX_GENERIC
+    auto pf = prime_factors(n);
+    if (pf.empty() || pf.back() > RMAX_GENERIC) return false;
+    std::vector<uint64_t> divs{1};
+    for (size_t i = 0; i < pf.size();) {
+        size_t j = i;
+        while (j < pf.size() && pf[j] == pf[i]) ++j;
+        size_t base = divs.size();
+        uint64_t pw = 1;
+        for (size_t e = 0; e < j - i; ++e) {
+            pw *= pf[i];
+            for (size_t k = 0; k < base; ++k) divs.push_back(divs[k] * pw);
+        }
+        i = j;
+    }
+    uint64_t best = 0;
+    for (auto d : divs)
+        if (d * d <= n && d > best) best = d;
+    if (best <= 1) return false;
+    n1 = best;
+    n2 = n / best;
+    const size_t esz = prec ? 16 : 8;
+    // the longer factor must still fit a tile of at least two lines
+    if ((n2 + (n2 >> 4) + 2) * esz * 2 > MAX_SMEM) return false;
+    return true;
+}
+
+void run_lines(const LineJob &job_in, cudaStream_t s) {
+    LineJob job = job_in;
+    if (job.n == 0) return;
+    std::vector<Dim> dims;
+    for (auto &d : job.batch) {
+        if (d.n == 0) return;
+        if (d.n >= (1ll << 31)) { set_error("array dimension too large"); throw Error(); }
+        if (d.n == 1) continue;
+        dims.push_back(d);
+    }
+    if (job.n >= (1ull << 31)) { set_error("transform length too large"); throw Error(); }
+    bool have_tw = false;
+    for (auto &d : dims) have_tw = have_tw || d.tw;
+    if (!have_tw) job.twN = 0;
+    std::stable_sort(dims.begin(), dims.end(), [](const Dim &a, const Dim &b) {
+        return std::min(iabs64(a.is), iabs64(a.os)) < std::min(iabs64(b.is), iabs64(b.os));
+    });
+    if (total_lines(dims) >= (1ull << 31)) { set_error("too many lines"); throw Error(); }
+
+    const bool simple = (job.load_mode == LD_C2C || job.load_mode == LD_REAL) && job.store_mode == ST_C2C &&
+                        job.flags == 0 && (job.n_in == 0 || job.n_in == job.n);
+    const size_t esz = job.prec ? 16 : 8;
+    TilePlan tp;
+    bool tile_ok = plan_tile(job, dims, tp);
+    if (tile_ok && simple && (tp.load_lf || tp.store_lf) && job.twN == 0) {
+        // strided long lines: a tile of >= 32 bytes per row does not fit -> four-step keeps
+        // the accesses coalesced
+        const uint32_t wmin = (uint32_t)(32 / esz) * 2;
+        uint64_t a, b;
+        if (tp.W < wmin && tp.W < dims[0].n && job.n >= 1024 && choose_split(job.n, job.prec, a, b)) tile_ok = false;
+    }
+    if (tile_ok) {
+        launch_tile(job, dims, tp, s);
+        return;
+    }
+    if (!simple) {
+        run_via_scratch(job, dims, s);
+        return;
+    }
+    if (job.twN) { set_error("internal: nested four-step"); throw Error(); }
+    uint64_t n1, n2;
+    if (choose_split(job.n, job.prec, n1, n2)) run_fourstep(job, dims, s);
+    else run_bluestein(job, dims, s);
+}
+
+static void run_via_scratch(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    const size_t esz = job.prec ? 16 : 8;
+    const uint64_t L = total_lines(dims);
+    const uint64_t n = job.n;
+    Scratch sc(L * n * esz, s);
+    BatchIdx bi = make_batch_idx(dims);
+    const bool al = alignment_ok(job, dims);
+    const uint32_t n_in = (uint32_t)(job.n_in ? job.n_in : n);
+    dim3 grid = ew_grid(n, L);
+    if (job.prec) {
+        if (al) gather_lines_kernel<double, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (double2 *)sc.p, (uint32_t)n, n_in, job.load_mode, job.flags);
+        else gather_lines_kernel<double, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (double2 *)sc.p, (uint32_t)n, n_in, job.load_mode, job.flags);
+    } else {
+        if (al) gather_lines_kernel<float, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (float2 *)sc.p, (uint32_t)n, n_in, job.load_mode, job.flags);
+        else gather_lines_kernel<float, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (float2 *)sc.p, (uint32_t)n, n_in, job.load_mode, job.flags);
+    }
+    RFB_AFTER_LAUNCH();
+    LineJob mid;
+    mid.prec = job.prec;
+    mid.n = n;
+    mid.is = mid.os = (int64_t)esz;
+    mid.batch.push_back(Dim{(int64_t)L, (int64_t)(n * esz), (int64_t)(n * esz), false});
+    mid.in = (const char *)sc.p;
+    mid.out = (char *)sc.p;
+    mid.backward = job.backward;
+    mid.fct = job.fct;
+    run_lines(mid, s);
+    const uint32_t n_out = (job.store_mode == ST_HALF) ? (uint32_t)(n / 2 + 1) : (uint32_t)n;
+    grid = ew_grid(n_out, L);
+    if (job.prec) {
+        if (al) scatter_lines_kernel<double, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const double2 *)sc.p, job.out, job.os, (uint32_t)n, n_out, job.store_mode, job.flags);
+        else scatter_lines_kernel<double, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const double2 *)sc.p, job.out, job.os, (uint32_t)n, n_out, job.store_mode, job.flags);
+    } else {
+        if (al) scatter_lines_kernel<float, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const float2 *)sc.p, job.out, job.os, (uint32_t)n, n_out, job.store_mode, job.flags);
+        else scatter_lines_kernel<float, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const float2 *)sc.p, job.out, job.os, (uint32_t)n, n_out, job.store_mode, job.flags);
+    }
+    RFB_AFTER_LAUNCH();
+}
+
+static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    const size_t esz = job.prec ? 16 : 8;
+    uint64_t n1, n2;
+    choose_split(job.n, job.prec, n1, n2);
+    const uint64_t L = total_lines(dims);
+    Scratch sc(L * job.n * esz, s);
+    // A: for every residue j0 (mod n2) an n1-point DFT over j1 of x[j1*n2 + j0], times
+    //    exp(-2 pi i j0 k1 / n), stored at scratch[k1*n2 + j0]
+    LineJob A;
+    A.prec = job.prec;
+    A.n = n1;
+    A.is = (int64_t)n2 * job.is;
+    A.os = (int64_t)(n2 * esz);
+    A.batch = contiguous_batch(dims, job.n * esz, false);
+    for (auto &d : A.batch) d.tw = false;
+    A.batch.push_back(Dim{(int64_t)n2, job.is, (int64_t)esz, true});
+    A.in = job.in;
+    A.out = (char *)sc.p;
+    A.backward = job.backward;
+    A.fct = 1.0;
+    A.load_mode = job.load_mode;
+    A.twN = job.n;
+    run_lines(A, s);
+    // B: for every k1 an n2-point DFT over j0 of scratch[k1*n2 + j0] -> X[k2*n1 + k1]
+    LineJob B;
+    B.prec = job.prec;
+    B.n = n2;
+    B.is = (int64_t)esz;
+    B.os = (int64_t)n1 * job.os;
+    B.batch = contiguous_batch(dims, job.n * esz, true);
+    for (auto &d : B.batch) d.tw = false;
+    B.batch.push_back(Dim{(int64_t)n1, (int64_t)(n2 * esz), job.os, false});
+    B.in = (const char *)sc.p;
+    B.out = job.out;
+    B.backward = job.backward;
+    B.fct = job.fct;
+    run_lines(B, s);
+}
+
+static std::mutex g_blue_mu;
+
+static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    if (job.load_mode != LD_C2C) {
+        // real input: go through the gather path first
+        run_via_scratch(job, dims, s);
+        return;
+    }
+    const size_t esz = job.prec ? 16 : 8;
+    const uint64_t n = job.n;
+    uint64_t M = 1;
+    while (M < 2 * n - 1) M <<= 1;
+    const uint64_t L = total_lines(dims);
+    const void *chirp = get_table(TAB_CHIRP, job.prec, n, 0);
+    const void *bhat;
+    {
+        std::lock_guard<std::mutex> lk(g_blue_mu);
+        bool created = false;
+        void *w = nullptr;
+        bhat = get_table(TAB_CHIRP_FFT, job.prec, n, M, &created, &w);
+        if (created) {
+            dim3 grid((unsigned)((M + 255) / 256));
+            if (job.prec) blue_kernel_seq<double><<<grid, 256, 0, s>>>((double2 *)w, (uint32_t)n, (uint32_t)M, (const double2 *)chirp);
+            else blue_kernel_seq<float><<<grid, 256, 0, s>>>((float2 *)w, (uint32_t)n, (uint32_t)M, (const float2 *)chirp);
+            RFB_AFTER_LAUNCH();
+            LineJob f;
+            f.prec = job.prec;
+            f.n = M;
+            f.is = f.os = (int64_t)esz;
+            f.in = (const char *)w;
+            f.out = (char *)w;
+            run_lines(f, s);
+            RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+    }
+    // process the lines in chunks so the padded work area stays bounded (<= ~2 GiB)
+    const uint64_t max_lines = std::max<uint64_t>(1, (2ull << 30) / (M * esz));
+    if (L > max_lines && dims.size() >= 1) {
+        // split along the outermost batch dim
+        std::vector<Dim> inner(dims.begin(), dims.end() - 1);
+        const Dim &o = dims.back();
+        const uint64_t inner_lines = total_lines(inner);
+        const uint64_t step = std::max<uint64_t>(1, max_lines / std::max<uint64_t>(1, inner_lines));
+        if (step < (uint64_t)o.n) {
+            for (int64_t i = 0; i < o.n; i += (int64_t)step) {
+                LineJob sub = job;
+                sub.batch = inner;
+                sub.batch.push_back(Dim{std::min<int64_t>((int64_t)step, o.n - i), o.is, o.os, false});
+                sub.in = job.in + i * o.is;
+                sub.out = job.out + i * o.os;
+                run_lines(sub, s);
+            }
+            return;
+        }
+    }
+    Scratch sc(L * M * esz, s);
+    BatchIdx bi = make_batch_idx(dims);
+    const bool al = alignment_ok(job, dims);
+    dim3 grid = ew_grid(M, L);
+    const int bw = job.backward ? 1 : 0;
+    if (job.prec) {
+        if (al) blue_pre_kernel<double, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (double2 *)sc.p, (uint32_t)n, (uint32_t)M, (const double2 *)chirp, bw);
+        else blue_pre_kernel<double, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (double2 *)sc.p, (uint32_t)n, (uint32_t)M, (const double2 *)chirp, bw);
+    } else {
+        if (al) blue_pre_kernel<float, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (float2 *)sc.p, (uint32_t)n, (uint32_t)M, (const float2 *)chirp, bw);
+        else blue_pre_kernel<float, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, job.in, job.is, (float2 *)sc.p, (uint32_t)n, (uint32_t)M, (const float2 *)chirp, bw);
+    }
+    RFB_AFTER_LAUNCH();
+    LineJob f;
+    f.prec = job.prec;
+    f.n = M;
+    f.is = f.os = (int64_t)esz;
+    f.batch.push_back(Dim{(int64_t)L, (int64_t)(M * esz), (int64_t)(M * esz), false});
+    f.in = (const char *)sc.p;
+    f.out = (char *)sc.p;
+    run_lines(f, s);
+    if (job.prec) blue_mul_kernel<double><<<grid, 256, 0, s>>>((double2 *)sc.p, (uint32_t)L, (uint32_t)M, (const double2 *)bhat);
+    else blue_mul_kernel<float><<<grid, 256, 0, s>>>((float2 *)sc.p, (uint32_t)L, (uint32_t)M, (const float2 *)bhat);
+    RFB_AFTER_LAUNCH();
+    f.backward = true;
+    run_lines(f, s);
+    grid = ew_grid(n, L);
+    if (job.prec) {
+        if (al) blue_post_kernel<double, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const double2 *)sc.p, job.out, job.os, (uint32_t)n, (uint32_t)M, (const double2 *)chirp, (double)job.fct, bw);
+        else blue_post_kernel<double, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const double2 *)sc.p, job.out, job.os, (uint32_t)n, (uint32_t)M, (const double2 *)chirp, (double)job.fct, bw);
+    } else {
+        if (al) blue_post_kernel<float, true><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const float2 *)sc.p, job.out, job.os, (uint32_t)n, (uint32_t)M, (const float2 *)chirp, (float)job.fct, bw);
+        else blue_post_kernel<float, false><<<grid, 256, 0, s>>>(bi, (uint32_t)L, (const float2 *)sc.p, job.out, job.os, (uint32_t)n, (uint32_t)M, (const float2 *)chirp, (float)job.fct, bw);
+    }
+    RFB_AFTER_LAUNCH();
+}
+
+}  // namespace rfb

@@ -1,0 +1,71 @@
+// Internal interface of the transform engine (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "modes.h"
+#include "plan.h"
+
+namespace rfb {
+
+struct Dim {
+    int64_t n;    // extent
+    int64_t is;   // input stride, bytes
+    int64_t os;   // output stride, bytes
+    bool tw;      // this dim's coordinate drives the four-step factor
+};
+
+// One batched 1-D complex DFT over strided memory.
+struct LineJob {
+    int prec = 0;        // 0: float, 1: double
+    uint64_t n = 0;      // transform length
+    int64_t is = 0, os = 0;
+    std::vector<Dim> batch;
+    const char *in = nullptr;
+    char *out = nullptr;
+    bool backward = false;
+    double fct = 1.0;
+    int load_mode = LD_C2C, store_mode = ST_C2C;
+    int flags = 0;
+    uint64_t n_in = 0;   // input elements present per line (0: n); the rest is zero padding
+    uint64_t twN = 0;    // four-step factor exp(-2 pi i c k / twN) on the output (0: none)
+};
+
+void run_lines(const LineJob &job, cudaStream_t stream);
+
+// N-D array description as it arrives through the ABI.
+struct NdArgs {
+    int prec;
+    std::vector<int64_t> shape, sin, sout;
+    std::vector<uint64_t> axes;
+    const char *in;
+    char *out;
+    double fct;
+};
+
+void op_c2c(const NdArgs &a, bool forward, cudaStream_t s);
+void op_r2c(const NdArgs &a, bool forward, cudaStream_t s);      // shape = real input shape
+void op_c2r(const NdArgs &a, bool forward, cudaStream_t s);      // shape = real output shape
+void op_c2c_sym(const NdArgs &a, bool forward, cudaStream_t s);
+void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s);
+void op_fftpack(const NdArgs &a, bool r2h, bool forward, cudaStream_t s);
+void op_separable_hartley(const NdArgs &a, cudaStream_t s);
+void op_genuine_hartley(const NdArgs &a, cudaStream_t s);
+
+uint64_t launch_count();
+void launch_count_reset();
+void set_dst_ortho_quirk(bool on);
+
+// stream-ordered scratch
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    Scratch(size_t bytes, cudaStream_t st);
+    ~Scratch();
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+};
+
+}  // namespace rfb

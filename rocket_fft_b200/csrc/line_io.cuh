@@ -1,0 +1,73 @@
+// How one element of a line is fetched from / delivered to global memory for every
+// load/store mode of the line engine.  Shared by the tile kernel (fused) and the
+// stand-alone gather/scatter kernels (long lines that go through scratch).
+#pragma once
+#include "common.cuh"
+#include "modes.h"
+
+namespace rfb {
+
+// element e (0 <= e < n) of the complex line the transform sees
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ cx<T> load_value(int mode, int flags, const char *line, int64_t sa, uint32_t e,
+                                            uint32_t n, uint32_t n_in) {
+    using C = cx<T>;
+    C val = mk<T>(T(0), T(0));
+    switch (mode) {
+        case LD_C2C:
+            if (e < n_in) val = ld_cx<T, ALIGNED>(line + (int64_t)e * sa);
+            break;
+        case LD_REAL:
+            if (e < n_in) {
+                val.x = *reinterpret_cast<const T *>(line + (int64_t)e * sa);
+                if ((flags & FLAG_NEG_EVEN_IN) && e >= 2 && !(e & 1)) val.x = -val.x;
+            }
+            break;
+        case LD_HERM: {
+            // Hermitian extension of bins 0..n/2; Im of bin 0 (and of bin n/2, n even) ignored
+            // (reference: general_c2r, _pocketfft_hdronly.h:3830, 3845-3846)
+            const bool upper = 2 * e > n;
+            const uint32_t k = upper ? n - e : e;
+            val = ld_cx<T, ALIGNED>(line + (int64_t)k * sa);
+            if (k == 0 || 2 * k == n) val.y = T(0);
+            if (upper) val.y = -val.y;
+            break;
+        }
+        case LD_HC: {
+            // FFTPACK halfcomplex [r0, r1, i1, r2, i2, ..., (r_{n/2})]
+            const bool upper = 2 * e > n;
+            const uint32_t k = upper ? n - e : e;
+            auto at = [&](uint32_t j) { return *reinterpret_cast<const T *>(line + (int64_t)j * sa); };
+            val.x = (k == 0) ? at(0) : at(2 * k - 1);
+            val.y = (k == 0 || 2 * k == n) ? T(0) : at(2 * k);
+            if (upper) val.y = -val.y;
+            break;
+        }
+    }
+    return val;
+}
+
+// which spectrum bin feeds output slot j
+__device__ __forceinline__ uint32_t store_bin(int mode, uint32_t j) {
+    return mode == ST_HC ? (j + 1) >> 1 : j;
+}
+
+// deliver output slot j given the (already scaled, un-swapped) spectrum value
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void store_value(int mode, int flags, char *line, int64_t sa, uint32_t j, cx<T> val) {
+    char *p = line + (int64_t)j * sa;
+    switch (mode) {
+        case ST_C2C:
+        case ST_HALF: st_cx<T, ALIGNED>(p, val); break;
+        case ST_REAL: {
+            T r = val.x;
+            if ((flags & FLAG_NEG_EVEN_OUT) && j >= 2 && !(j & 1)) r = -r;
+            *reinterpret_cast<T *>(p) = r;
+            break;
+        }
+        case ST_HC: *reinterpret_cast<T *>(p) = (j == 0 || (j & 1)) ? val.x : val.y; break;
+        case ST_HARTLEY: *reinterpret_cast<T *>(p) = val.x + val.y; break;
+    }
+}
+
+}  // namespace rfb

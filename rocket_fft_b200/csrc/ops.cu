@@ -1,0 +1,511 @@
+// N-D drivers: what each entry point of the C ABI does in terms of line jobs.
+// Semantics follow the reference's public templates (_pocketfft_hdronly.h:3875-4091) and
+// its boundary file (_pocketfft_numba.cpp:25-223); see SURVEY.md section 8(a).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace rfb {
+
+static bool g_dst_quirk = true;
+void set_dst_ortho_quirk(bool on) { g_dst_quirk = on; }
+
+#define RFB_AFTER_LAUNCH2() RFB_CUDA_CHECK(cudaGetLastError())
+extern void count_launch();
+
+static bool any_zero(const std::vector<int64_t> &s) {
+    for (auto v : s)
+        if (v == 0) return true;
+    return false;
+}
+
+static std::vector<Dim> batch_dims(const std::vector<int64_t> &shape, const std::vector<int64_t> &is,
+                                   const std::vector<int64_t> &os, size_t axis) {
+    std::vector<Dim> b;
+    for (size_t d = 0; d < shape.size(); ++d)
+        if (d != axis) b.push_back(Dim{shape[d], is[d], os[d], false});
+    return b;
+}
+
+static std::vector<int64_t> c_strides(const std::vector<int64_t> &shape, int64_t esz) {
+    std::vector<int64_t> st(shape.size());
+    int64_t acc = esz;
+    for (size_t i = shape.size(); i-- > 0;) {
+        st[i] = acc;
+        acc *= std::max<int64_t>(shape[i], 1);
+    }
+    return st;
+}
+
+static uint64_t prod(const std::vector<int64_t> &s) {
+    uint64_t p = 1;
+    for (auto v : s) p *= (uint64_t)v;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------
+// c2c  (reference: c2c H:3875-3889 -> general_nd H:3568-3607: axes in the given order,
+// first axis reads `in`, later ones work on `out`; fct applied once)
+// ---------------------------------------------------------------------------------------
+static void c2c_axes(int prec, const std::vector<int64_t> &shape, const std::vector<int64_t> &sin,
+                     const std::vector<int64_t> &sout, const uint64_t *axes, size_t naxes, const char *in, char *out,
+                     bool forward, double fct, cudaStream_t s) {
+    bool first = true;
+    for (size_t i = 0; i < naxes; ++i) {
+        const size_t ax = (size_t)axes[i];
+        LineJob j;
+        j.prec = prec;
+        j.n = (uint64_t)shape[ax];
+        j.in = first ? in : out;
+        j.out = out;
+        const auto &si = first ? sin : sout;
+        j.is = si[ax];
+        j.os = sout[ax];
+        j.batch = batch_dims(shape, si, sout, ax);
+        j.backward = !forward;
+        j.fct = first ? fct : 1.0;
+        run_lines(j, s);
+        first = false;
+    }
+}
+
+void op_c2c(const NdArgs &a, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape)) return;
+    c2c_axes(a.prec, a.shape, a.sin, a.sout, a.axes.data(), a.axes.size(), a.in, a.out, forward, a.fct, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// r2c  (reference: r2c H:3955-3975: real transform along axes.back(), then c2c in place on
+// the half-spectrum array over the remaining axes, fct applied by the real transform)
+// ---------------------------------------------------------------------------------------
+static void r2c_into(int prec, const std::vector<int64_t> &shape_in, const std::vector<int64_t> &sin,
+                     const std::vector<int64_t> &sout, const std::vector<uint64_t> &axes, const char *in, char *out,
+                     bool forward, double fct, cudaStream_t s) {
+    const size_t L = (size_t)axes.back();
+    LineJob j;
+    j.prec = prec;
+    j.n = (uint64_t)shape_in[L];
+    j.in = in;
+    j.out = out;
+    j.is = sin[L];
+    j.os = sout[L];
+    j.batch = batch_dims(shape_in, sin, sout, L);
+    j.backward = !forward;
+    j.fct = fct;
+    j.load_mode = LD_REAL;
+    j.store_mode = ST_HALF;
+    run_lines(j, s);
+    if (axes.size() > 1) {
+        std::vector<int64_t> shape_out = shape_in;
+        shape_out[L] = shape_in[L] / 2 + 1;
+        c2c_axes(prec, shape_out, sout, sout, axes.data(), axes.size() - 1, out, out, forward, 1.0, s);
+    }
+}
+
+void op_r2c(const NdArgs &a, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape) || a.axes.empty()) return;
+    r2c_into(a.prec, a.shape, a.sin, a.sout, a.axes, a.in, a.out, forward, a.fct, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// c2r  (reference: c2r H:3995-4023: c2c over axes[:-1] into a contiguous temporary, then the
+// Hermitian -> real transform along axes.back(); shape is the OUTPUT's)
+// ---------------------------------------------------------------------------------------
+void op_c2r(const NdArgs &a, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape) || a.axes.empty()) return;
+    const size_t L = (size_t)a.axes.back();
+    const int64_t esz = a.prec ? 16 : 8;
+    const char *src = a.in;
+    std::vector<int64_t> ssrc = a.sin;
+    std::vector<int64_t> shape_in = a.shape;
+    shape_in[L] = a.shape[L] / 2 + 1;
+    Scratch *tmp = nullptr;
+    struct Guard { Scratch *&p; ~Guard() { delete p; } } guard{tmp};
+    if (a.axes.size() > 1) {
+        std::vector<int64_t> st = c_strides(shape_in, esz);
+        tmp = new Scratch(prod(shape_in) * (uint64_t)esz, s);
+        c2c_axes(a.prec, shape_in, a.sin, st, a.axes.data(), a.axes.size() - 1, a.in, (char *)tmp->p, forward, 1.0, s);
+        src = (const char *)tmp->p;
+        ssrc = st;
+    }
+    LineJob j;
+    j.prec = a.prec;
+    j.n = (uint64_t)a.shape[L];
+    j.in = src;
+    j.out = a.out;
+    j.is = ssrc[L];
+    j.os = a.sout[L];
+    j.batch = batch_dims(a.shape, ssrc, a.sout, L);
+    j.backward = !forward;
+    j.fct = a.fct;
+    j.load_mode = LD_HERM;
+    j.store_mode = ST_REAL;
+    run_lines(j, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// N-D index helper for the mirror / Hartley-combine kernels
+// ---------------------------------------------------------------------------------------
+struct NdIdx {
+    int nd;
+    uint32_t ext[8];    // iteration extents (dim nd-1 fastest)
+    uint32_t full[8];   // full extents
+    FastDiv d[8];
+    int64_t sa[8], sb[8];
+    int rev[8];         // index negated (mod full) along this dim when mirroring
+    int L;              // the halved axis
+    uint32_t l_first;   // first index along L covered by the iteration
+};
+
+// out[idx] = conj(out[mirror(idx)]) for all idx with idx_L > n_L/2
+// (reference: numba_c2c_sym, _pocketfft_numba.cpp:123-129, rev_iter H:3383-3444)
+template <typename T>
+__global__ void mirror_fill_kernel(NdIdx ix, uint64_t total, char *out) {
+    for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t rem = f;
+        int64_t dst = 0, src = 0;
+        for (int d = ix.nd - 1; d >= 0; --d) {
+            uint32_t i = (uint32_t)(rem % ix.ext[d]);
+            rem /= ix.ext[d];
+            if (d == ix.L) i += ix.l_first;
+            uint32_t m = ix.rev[d] ? (i == 0 ? 0 : ix.full[d] - i) : i;
+            dst += (int64_t)i * ix.sa[d];
+            src += (int64_t)m * ix.sa[d];
+        }
+        const T *p = reinterpret_cast<const T *>(out + src);
+        T re = p[0], im = p[1];
+        T *q = reinterpret_cast<T *>(out + dst);
+        q[0] = re;
+        q[1] = -im;
+    }
+}
+
+// out[idx] = Re + Im of tmp[idx] (idx_L <= n_L/2) or Re - Im of tmp[mirror(idx)]
+// (reference: r2r_genuine_hartley H:4078-4090)
+template <typename T>
+__global__ void hartley_combine_kernel(NdIdx ix, uint64_t total, const char *tmp, char *out) {
+    for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t rem = f;
+        int64_t dst = 0, src = 0, srcm = 0;
+        bool upper = false;
+        for (int d = ix.nd - 1; d >= 0; --d) {
+            uint32_t i = (uint32_t)(rem % ix.ext[d]);
+            rem /= ix.ext[d];
+            uint32_t m = ix.rev[d] ? (i == 0 ? 0 : ix.full[d] - i) : i;
+            if (d == ix.L && 2 * i > ix.full[d]) upper = true;
+            dst += (int64_t)i * ix.sb[d];
+            src += (int64_t)i * ix.sa[d];
+            srcm += (int64_t)m * ix.sa[d];
+        }
+        const T *p = reinterpret_cast<const T *>(tmp + (upper ? srcm : src));
+        *reinterpret_cast<T *>(out + dst) = upper ? (p[0] - p[1]) : (p[0] + p[1]);
+    }
+}
+
+static NdIdx make_ndidx(const std::vector<int64_t> &shape, const std::vector<int64_t> &sa,
+                        const std::vector<int64_t> &sb, const std::vector<uint64_t> &axes) {
+    NdIdx ix;
+    memset(&ix, 0, sizeof(ix));
+    if (shape.size() > 8) { set_error("more than 8 array dimensions are not supported here"); throw Error(); }
+    ix.nd = (int)shape.size();
+    for (int d = 0; d < ix.nd; ++d) {
+        ix.ext[d] = ix.full[d] = (uint32_t)shape[d];
+        ix.sa[d] = sa[d];
+        ix.sb[d] = sb.empty() ? 0 : sb[d];
+    }
+    for (auto a : axes) ix.rev[a] = 1;
+    ix.L = (int)axes.back();
+    return ix;
+}
+
+static unsigned ew_blocks(uint64_t total) { return (unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32); }
+
+void op_c2c_sym(const NdArgs &a, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape) || a.axes.empty()) return;
+    r2c_into(a.prec, a.shape, a.sin, a.sout, a.axes, a.in, a.out, forward, a.fct, s);
+    NdIdx ix = make_ndidx(a.shape, a.sout, {}, a.axes);
+    const uint32_t nL = (uint32_t)a.shape[ix.L];
+    ix.l_first = nL / 2 + 1;
+    if (ix.l_first >= nL) return;
+    ix.ext[ix.L] = nL - ix.l_first;
+    uint64_t total = 1;
+    for (int d = 0; d < ix.nd; ++d) total *= ix.ext[d];
+    if (a.prec) mirror_fill_kernel<double><<<ew_blocks(total), 256, 0, s>>>(ix, total, a.out);
+    else mirror_fill_kernel<float><<<ew_blocks(total), 256, 0, s>>>(ix, total, a.out);
+    count_launch();
+    RFB_AFTER_LAUNCH2();
+}
+
+// ---------------------------------------------------------------------------------------
+// Hartley  (reference: H:4042-4091)
+// ---------------------------------------------------------------------------------------
+void op_separable_hartley(const NdArgs &a, cudaStream_t s) {
+    if (any_zero(a.shape)) return;
+    bool first = true;
+    for (auto axu : a.axes) {
+        const size_t ax = (size_t)axu;
+        LineJob j;
+        j.prec = a.prec;
+        j.n = (uint64_t)a.shape[ax];
+        j.in = first ? a.in : a.out;
+        j.out = a.out;
+        const auto &si = first ? a.sin : a.sout;
+        j.is = si[ax];
+        j.os = a.sout[ax];
+        j.batch = batch_dims(a.shape, si, a.sout, ax);
+        j.fct = first ? a.fct : 1.0;
+        j.load_mode = LD_REAL;
+        j.store_mode = ST_HARTLEY;
+        run_lines(j, s);
+        first = false;
+    }
+}
+
+void op_genuine_hartley(const NdArgs &a, cudaStream_t s) {
+    if (any_zero(a.shape) || a.axes.empty()) return;
+    if (a.axes.size() == 1) return op_separable_hartley(a, s);
+    const int64_t esz = a.prec ? 16 : 8;
+    const size_t L = (size_t)a.axes.back();
+    std::vector<int64_t> tshape = a.shape;
+    tshape[L] = a.shape[L] / 2 + 1;
+    std::vector<int64_t> tst = c_strides(tshape, esz);
+    Scratch tmp(prod(tshape) * (uint64_t)esz, s);
+    r2c_into(a.prec, a.shape, a.sin, tst, a.axes, a.in, (char *)tmp.p, true, a.fct, s);
+    NdIdx ix = make_ndidx(a.shape, tst, a.sout, a.axes);
+    uint64_t total = prod(a.shape);
+    if (a.prec) hartley_combine_kernel<double><<<ew_blocks(total), 256, 0, s>>>(ix, total, (const char *)tmp.p, a.out);
+    else hartley_combine_kernel<float><<<ew_blocks(total), 256, 0, s>>>(ix, total, (const char *)tmp.p, a.out);
+    count_launch();
+    RFB_AFTER_LAUNCH2();
+}
+
+// ---------------------------------------------------------------------------------------
+// r2r_fftpack  (reference: H:4025-4040 + ExecR2R H:3854-3873).  The reference executes the
+// real plan in direction `forward` whatever `real2hermitian` says (H:3867), so:
+//   (r2h, fwd) = (T,T): real -> halfcomplex, sign -         (T,F): hc -> real, then negate 2,4,..
+//                (F,F): halfcomplex -> real, sign +         (F,T): negate 2,4,.. then real -> hc
+// ---------------------------------------------------------------------------------------
+void op_fftpack(const NdArgs &a, bool r2h, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape)) return;
+    bool first = true;
+    for (auto axu : a.axes) {
+        const size_t ax = (size_t)axu;
+        LineJob j;
+        j.prec = a.prec;
+        j.n = (uint64_t)a.shape[ax];
+        j.in = first ? a.in : a.out;
+        j.out = a.out;
+        const auto &si = first ? a.sin : a.sout;
+        j.is = si[ax];
+        j.os = a.sout[ax];
+        j.batch = batch_dims(a.shape, si, a.sout, ax);
+        j.fct = first ? a.fct : 1.0;
+        if (forward) {
+            j.load_mode = LD_REAL;
+            j.store_mode = ST_HC;
+            j.backward = false;
+            if (!r2h) j.flags |= FLAG_NEG_EVEN_IN;
+        } else {
+            j.load_mode = LD_HC;
+            j.store_mode = ST_REAL;
+            j.backward = true;
+            if (r2h) j.flags |= FLAG_NEG_EVEN_OUT;
+        }
+        run_lines(j, s);
+        first = false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// DCT / DST types 1-4  (reference: dct H:3891-3912, dst H:3914-3935, T_dct1 2918,
+// T_dst1 2957, T_dcst23 2987, T_dcst4 3063).  Each line is embedded into a complex sequence
+// of length Lf (2(N-1), 2(N+1) or 2N), transformed by the line engine, and read back with
+// the type's phase factor:  see DESIGN.md "DCT/DST" for the identities.
+// ---------------------------------------------------------------------------------------
+struct DcstParams {
+    uint32_t N, Lf;
+    int type, cosine, ortho, quirk;
+};
+
+struct LinesIdx {
+    int nd;
+    uint32_t ext[8];
+    FastDiv d[8];
+    int64_t is[8], os[8];
+};
+
+__device__ __forceinline__ void lines_off(const LinesIdx &bi, uint32_t l, int64_t &oi, int64_t &oo) {
+    oi = 0; oo = 0;
+    for (int d = 0; d < bi.nd; ++d) {
+        uint32_t q, r;
+        fdivmod(l, bi.d[d], q, r);
+        oi += (int64_t)r * bi.is[d];
+        oo += (int64_t)r * bi.os[d];
+        l = q;
+    }
+}
+
+// exp(-i pi num / den) evaluated in double
+__device__ __forceinline__ double2 cis_mpi(double num, double den) {
+    double sn, cs;
+    sincospi(num / den, &sn, &cs);
+    return make_double2(cs, -sn);
+}
+
+template <typename T>
+__global__ void dcst_pre_kernel(LinesIdx bi, uint32_t nlines, const char *in, int64_t sa, cx<T> *z, DcstParams p) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.Lf) return;
+    const uint32_t N = p.N;
+    const double SQ2 = 1.4142135623730951;
+    for (uint32_t l = blockIdx.y; l < nlines; l += gridDim.y) {
+        int64_t oi, oo;
+        lines_off(bi, l, oi, oo);
+        auto x = [&](uint32_t i) { return (double)*reinterpret_cast<const T *>(in + oi + (int64_t)i * sa); };
+        double re = 0.0, im = 0.0;
+        if (p.type == 1) {
+            if (p.cosine) {
+                const uint32_t i = (e <= N - 1) ? e : p.Lf - e;
+                re = x(i);
+                if (p.ortho && (i == 0 || i == N - 1)) re *= SQ2;
+            } else {
+                if (e == 0 || e == N + 1) re = 0.0;
+                else if (e <= N) re = x(e - 1);
+                else re = -x(p.Lf - e - 1);
+            }
+        } else if (e < N) {
+            // sine variants read the line reversed (types 3, 4) or with alternating sign (type 2)
+            if (p.type == 2) {
+                re = x(e);
+                if (!p.cosine && (e & 1)) re = -re;
+            } else {
+                const uint32_t i = p.cosine ? e : N - 1 - e;
+                double v = x(i);
+                if (p.type == 3) {
+                    // coefficient 1 for the transform's element 0, 2 otherwise; ortho scales one
+                    // element by sqrt(2): index 0 of the line as the caller sees it for the cosine
+                    // transform -- and, reproducing the reference, for the sine transform as well
+                    // (SciPy scales the caller's index N-1 there)
+                    if (e != 0) v *= 2.0;
+                    if (p.ortho) {
+                        const uint32_t scaled = p.cosine ? 0u : (p.quirk ? 0u : N - 1);
+                        if (i == scaled) v *= SQ2;
+                    }
+                }
+                const double2 w = cis_mpi((double)e, 2.0 * (double)N);
+                re = v * w.x;
+                im = v * w.y;
+            }
+        }
+        z[(size_t)l * p.Lf + e] = mk<T>((T)re, (T)im);
+    }
+}
+
+template <typename T>
+__global__ void dcst_post_kernel(LinesIdx bi, uint32_t nlines, const cx<T> *z, char *out, int64_t sa, DcstParams p) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t N = p.N;
+    if (k >= N) return;
+    const double RSQ2 = 0.70710678118654752;
+    for (uint32_t l = blockIdx.y; l < nlines; l += gridDim.y) {
+        int64_t oi, oo;
+        lines_off(bi, l, oi, oo);
+        const cx<T> *zl = z + (size_t)l * p.Lf;
+        double y;
+        if (p.type == 1) {
+            if (p.cosine) {
+                y = (double)zl[k].x;
+                if (p.ortho && (k == 0 || k == N - 1)) y *= RSQ2;
+            } else y = -(double)zl[k + 1].y;
+        } else if (p.type == 2) {
+            const uint32_t kk = p.cosine ? k : N - 1 - k;
+            const double2 w = cis_mpi((double)kk, 2.0 * (double)N);
+            const cx<T> v = zl[kk];
+            y = 2.0 * ((double)v.x * w.x - (double)v.y * w.y);
+            if (p.ortho) {
+                const uint32_t scaled = p.cosine ? 0u : (p.quirk ? 0u : N - 1);
+                if (k == scaled) y *= RSQ2;
+            }
+        } else if (p.type == 3) {
+            y = (double)zl[k].x;
+            if (!p.cosine && (k & 1)) y = -y;
+        } else {
+            const double2 w = cis_mpi((double)(2 * k + 1), 4.0 * (double)N);
+            const cx<T> v = zl[k];
+            y = 2.0 * ((double)v.x * w.x - (double)v.y * w.y);
+            if (!p.cosine && (k & 1)) y = -y;
+        }
+        *reinterpret_cast<T *>(out + oo + (int64_t)k * sa) = (T)y;
+    }
+}
+
+void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s) {
+    if (any_zero(a.shape)) return;
+    if (type < 1 || type > 4) { set_error("invalid DCT/DST type"); throw Error(); }
+    const int64_t esz = a.prec ? 16 : 8;
+    bool first = true;
+    for (auto axu : a.axes) {
+        const size_t ax = (size_t)axu;
+        const uint64_t N = (uint64_t)a.shape[ax];
+        DcstParams p;
+        p.N = (uint32_t)N;
+        p.type = type;
+        p.cosine = cosine ? 1 : 0;
+        p.ortho = ortho ? 1 : 0;
+        p.quirk = g_dst_quirk ? 1 : 0;
+        if (type == 1) {
+            if (cosine && N < 2) { set_error("DCT-I needs at least two points (zero-length FFT requested)"); throw Error(); }
+            p.Lf = (uint32_t)(cosine ? 2 * (N - 1) : 2 * (N + 1));
+        } else p.Lf = (uint32_t)(2 * N);
+        const auto &si = first ? a.sin : a.sout;
+        std::vector<Dim> b = batch_dims(a.shape, si, a.sout, ax);
+        LinesIdx bi;
+        memset(&bi, 0, sizeof(bi));
+        uint64_t nlines = 1;
+        {
+            int k = 0;
+            for (auto &d : b) {
+                if (d.n == 1) continue;
+                if (k >= 8) { set_error("more than 9 array dimensions are not supported"); throw Error(); }
+                bi.ext[k] = (uint32_t)d.n;
+                bi.d[k] = make_fastdiv((uint32_t)d.n);
+                bi.is[k] = d.is;
+                bi.os[k] = d.os;
+                nlines *= (uint64_t)d.n;
+                ++k;
+            }
+            bi.nd = k;
+        }
+        if (nlines >= (1ull << 31)) { set_error("too many lines"); throw Error(); }
+        // bounded work area: process the lines in slabs of <= ~1 GiB of scratch
+        const uint64_t per_line = (uint64_t)p.Lf * (uint64_t)esz;
+        Scratch sc(nlines * per_line, s);
+        const char *src = first ? a.in : a.out;
+        dim3 grid((unsigned)((p.Lf + 255) / 256), (unsigned)std::min<uint64_t>(nlines, 32768));
+        if (a.prec) dcst_pre_kernel<double><<<grid, 256, 0, s>>>(bi, (uint32_t)nlines, src, si[ax], (double2 *)sc.p, p);
+        else dcst_pre_kernel<float><<<grid, 256, 0, s>>>(bi, (uint32_t)nlines, src, si[ax], (float2 *)sc.p, p);
+        count_launch();
+        RFB_AFTER_LAUNCH2();
+        LineJob j;
+        j.prec = a.prec;
+        j.n = p.Lf;
+        j.is = j.os = esz;
+        j.batch.push_back(Dim{(int64_t)nlines, (int64_t)per_line, (int64_t)per_line, false});
+        j.in = (const char *)sc.p;
+        j.out = (char *)sc.p;
+        j.fct = first ? a.fct : 1.0;
+        run_lines(j, s);
+        dim3 grid2((unsigned)((N + 255) / 256), (unsigned)std::min<uint64_t>(nlines, 32768));
+        if (a.prec) dcst_post_kernel<double><<<grid2, 256, 0, s>>>(bi, (uint32_t)nlines, (const double2 *)sc.p, a.out, a.sout[ax], p);
+        else dcst_post_kernel<float><<<grid2, 256, 0, s>>>(bi, (uint32_t)nlines, (const float2 *)sc.p, a.out, a.sout[ax], p);
+        count_launch();
+        RFB_AFTER_LAUNCH2();
+        first = false;
+    }
+}
+
+}  // namespace rfb

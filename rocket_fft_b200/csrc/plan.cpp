@@ -1,0 +1,224 @@
+#include "plan.h"
+
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace rfb {
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+const char *last_error() { return g_err.c_str(); }
+void clear_error() { g_err.clear(); }
+
+// ---------------------------------------------------------------------------------------
+// good_size: smallest {2,3,5,7,11}-smooth (complex) / {2,3,5}-smooth (real) integer >= target.
+// Same function of (target, real) as numba_good_size in the reference
+// (_pocketfft_numba.cpp:25-29 -> _pocketfft_hdronly.h:589-650); small targets are returned
+// unchanged there (<= 12 complex, <= 6 real) and therefore here.  Depth-first enumeration of
+// smooth numbers with branch-and-bound on the best candidate so far.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct SmoothSearch {
+    unsigned __int128 target, best;
+    const uint32_t *primes;
+    int nprimes;
+    void go(int idx, unsigned __int128 val) {
+        if (val >= target) {
+            if (val < best) best = val;
+            return;
+        }
+        if (idx == nprimes) return;
+        for (unsigned __int128 v = val; v < best; v *= primes[idx]) go(idx + 1, v);
+    }
+};
+}  // namespace
+
+uint64_t good_size(uint64_t target, bool real) {
+    static const uint32_t pc[5] = {11, 7, 5, 3, 2};
+    static const uint32_t pr[3] = {5, 3, 2};
+    if (target <= (real ? 6u : 12u)) return target;
+    SmoothSearch s;
+    s.target = target;
+    s.best = 1;
+    while (s.best < s.target) s.best *= 2;
+    s.primes = real ? pr : pc;
+    s.nprimes = real ? 3 : 5;
+    s.go(0, 1);
+    return (uint64_t)s.best;
+}
+
+// ---------------------------------------------------------------------------------------
+// factorisation
+// ---------------------------------------------------------------------------------------
+std::vector<uint64_t> prime_factors(uint64_t n) {
+    std::vector<uint64_t> f;
+    while (n > 1 && (n & 1) == 0) { f.push_back(2); n >>= 1; }
+    for (uint64_t p = 3; p * p <= n; p += 2)
+        while (n % p == 0) { f.push_back(p); n /= p; }
+    if (n > 1) f.push_back(n);
+    return f;
+}
+
+uint64_t largest_prime_factor(uint64_t n) {
+    auto f = prime_factors(n);
+    return f.empty() ? 1 : f.back();
+}
+
+std::vector<uint32_t> radix_schedule(uint64_t n, uint32_t rmax) {
+    std::vector<uint32_t> sched;
+    auto f = prime_factors(n);
+    int e2 = 0;
+    std::vector<uint32_t> odd;
+    for (auto p : f) {
+        if (p == 2) ++e2;
+        else {
+            if (p > rmax) return {};
+            odd.push_back((uint32_t)p);
+        }
+    }
+    // group the twos: as many 16s as possible, remainder folded into 8/4 where that
+    // keeps every pass at radix >= 4
+    int n16 = e2 / 4, rem = e2 % 4;
+    if (rem == 1 && n16 > 0) { --n16; for (int i = 0; i < n16; ++i) sched.push_back(16); sched.push_back(8); sched.push_back(4); }
+    else {
+        for (int i = 0; i < n16; ++i) sched.push_back(16);
+        if (rem == 1) sched.push_back(2);
+        if (rem == 2) sched.push_back(4);
+        if (rem == 3) sched.push_back(8);
+    }
+    for (auto p : odd) sched.push_back(p);
+    if (sched.empty()) sched.push_back(1);  // n == 1
+    return sched;
+}
+
+// ---------------------------------------------------------------------------------------
+// exact trigonometry
+// ---------------------------------------------------------------------------------------
+void sincos_2pi(uint64_t num, uint64_t den, long double &c, long double &s) {
+    static const long double PI_4 = 0.78539816339744830961566084581987572L;
+    num %= den;
+    unsigned __int128 a = (unsigned __int128)num * 8u;
+    uint64_t oct = (uint64_t)(a / den);
+    uint64_t rem = (uint64_t)(a - (unsigned __int128)oct * den);
+    long double bc, bs;
+    uint64_t quarter;
+    if ((oct & 1) == 0) {
+        long double th = PI_4 * ((long double)rem / (long double)den);
+        bc = cosl(th); bs = sinl(th);
+        quarter = oct / 2;
+    } else {
+        long double th = PI_4 * ((long double)(den - rem) / (long double)den);
+        bc = cosl(th); bs = -sinl(th);
+        quarter = (oct + 1) / 2;
+    }
+    switch (quarter & 3) {
+        case 0: c = bc; s = bs; break;
+        case 1: c = -bs; s = bc; break;
+        case 2: c = -bc; s = -bs; break;
+        default: c = bs; s = -bc; break;
+    }
+}
+
+uint32_t split_size(uint64_t n) {
+    uint32_t s = 1;
+    while ((uint64_t)s * s < n) s <<= 1;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// device table cache
+// ---------------------------------------------------------------------------------------
+namespace {
+struct Key {
+    int dev, kind, prec;
+    uint64_t n, param;
+    bool operator<(const Key &o) const {
+        return std::tie(dev, kind, prec, n, param) < std::tie(o.dev, o.kind, o.prec, o.n, o.param);
+    }
+};
+std::mutex g_mu;
+std::map<Key, void *> g_tables;
+
+template <typename T>
+void fill(std::vector<T> &h, TableKind kind, uint64_t n, uint64_t param, size_t count) {
+    h.resize(2 * count);
+    for (size_t t = 0; t < count; ++t) {
+        long double c, s;
+        switch (kind) {
+            case TAB_LINE:
+            case TAB_SPLIT_B: sincos_2pi(t, n, c, s); break;
+            case TAB_SPLIT_A: sincos_2pi((uint64_t)(((unsigned __int128)t * param) % n), n, c, s); break;
+            case TAB_CHIRP: {
+                // exp(-i pi t^2 / n) = exp(-2 pi i (t^2 mod 2n) / (2n)), exact integer reduction
+                uint64_t m = (uint64_t)(((unsigned __int128)t * t) % (2 * (unsigned __int128)n));
+                sincos_2pi(m, 2 * n, c, s);
+                break;
+            }
+            case TAB_QUARTER: sincos_2pi(t, 4 * n, c, s); break;
+            default: c = 0; s = 0; break;
+        }
+        h[2 * t] = (T)c;
+        h[2 * t + 1] = (T)(-s);
+    }
+}
+}  // namespace
+
+const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool *created, void **writable) {
+    int dev = 0;
+    RFB_CUDA_CHECK(cudaGetDevice(&dev));
+    Key key{dev, (int)kind, prec, n, param};
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_tables.find(key);
+    if (created) *created = false;
+    if (it != g_tables.end()) {
+        if (writable) *writable = it->second;
+        return it->second;
+    }
+    size_t count = 0;
+    switch (kind) {
+        case TAB_LINE: count = n; break;
+        case TAB_SPLIT_A: count = (n + param - 1) / param + 1; break;
+        case TAB_SPLIT_B: count = param; break;
+        case TAB_CHIRP: count = n; break;
+        case TAB_CHIRP_FFT: count = param; break;
+        case TAB_QUARTER: count = n + 1; break;
+    }
+    size_t esz = prec ? 16 : 8;
+    void *d = nullptr;
+    RFB_CUDA_CHECK(cudaMalloc(&d, count * esz > 0 ? count * esz : esz));
+    if (kind != TAB_CHIRP_FFT) {
+        if (prec) {
+            std::vector<double> h;
+            fill(h, kind, n, param, count);
+            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), count * esz, cudaMemcpyHostToDevice));
+        } else {
+            std::vector<float> h;
+            fill(h, kind, n, param, count);
+            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), count * esz, cudaMemcpyHostToDevice));
+        }
+    }
+    g_tables[key] = d;
+    if (created) *created = true;
+    if (writable) *writable = d;
+    return d;
+}
+
+void plan_cache_clear() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto it = g_tables.begin(); it != g_tables.end();) {
+        if (it->first.dev == cur) {
+            cudaFree(it->second);
+            it = g_tables.erase(it);
+        } else ++it;
+    }
+}
+
+}  // namespace rfb

@@ -1,0 +1,225 @@
+"""Low-level transform API of rocket_fft_b200 -- same names, argument order and
+meaning as the reference's low-level interface (rocket_fft/__init__.py:18-34,
+rocket_fft/__init__.pyi:6-105; README.md:74-85):
+
+    c2c(ain, aout, axes, forward, fct, nthreads)        r2c / c2r / c2c_sym likewise
+    dct(ain, aout, axes, type, fct, ortho, nthreads)    dst likewise
+    r2r_separable_hartley(ain, aout, axes, fct, nthreads)   r2r_genuine_hartley likewise
+    r2r_fftpack(ain, aout, axes, real2hermitian, forward, fct, nthreads)
+    good_size(n, real)
+
+Arrays may be
+  * NumPy arrays (host): the call goes through the library's ``numba_*`` symbols --
+    the very entry points Numba-compiled code binds -- which stage H2D, run the
+    sm_100a kernels and copy the result back before returning;
+  * anything exporting ``__cuda_array_interface__`` (torch CUDA tensors, CuPy, Numba
+    device arrays): the ``rfb200_*`` device entry points run on the caller's current
+    CUDA stream with no copies.
+``nthreads`` is accepted for signature compatibility and ignored: the parallelism is
+the GPU's.  There is no CPU fallback; importing this module without the compiled
+library raises ImportError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librocketfft_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C rocket_fft_b200/csrc` (there is no CPU fallback)"
+    )
+
+lib = _abi.LowLevelLib(LIB_PATH)
+_c = lib.cdll
+
+_I64P = C.POINTER(C.c_int64)
+_U64P = C.POINTER(C.c_uint64)
+_DEV_COMMON = [C.c_int, C.c_size_t, _I64P, _I64P, _I64P, C.c_size_t, _U64P]
+_DEV_TAIL = [C.c_void_p, C.c_void_p, C.c_void_p]
+for _name, _mid in {
+    "rfb200_c2c": [C.c_int, C.c_double],
+    "rfb200_r2c": [C.c_int, C.c_double],
+    "rfb200_c2r": [C.c_int, C.c_double],
+    "rfb200_c2c_sym": [C.c_int, C.c_double],
+    "rfb200_dct": [C.c_int, C.c_double, C.c_int],
+    "rfb200_dst": [C.c_int, C.c_double, C.c_int],
+    "rfb200_r2r_fftpack": [C.c_int, C.c_int, C.c_double],
+    "rfb200_r2r_separable_hartley": [C.c_double],
+    "rfb200_r2r_genuine_hartley": [C.c_double],
+}.items():
+    _f = getattr(_c, _name)
+    _f.restype = C.c_int
+    _f.argtypes = _DEV_COMMON + _mid + _DEV_TAIL
+_c.rfb200_last_error.restype = C.c_char_p
+_c.rfb200_version.restype = C.c_char_p
+_c.rfb200_launch_count.restype = C.c_uint64
+_c.rfb200_set_stream.argtypes = [C.c_void_p]
+_c.rfb200_set_dst_ortho_quirk.argtypes = [C.c_int]
+
+
+class TransformError(RuntimeError):
+    pass
+
+
+def last_error() -> str:
+    return (_c.rfb200_last_error() or b"").decode()
+
+
+def version() -> str:
+    return _c.rfb200_version().decode()
+
+
+def launch_count() -> int:
+    return int(_c.rfb200_launch_count())
+
+
+def launch_count_reset() -> None:
+    _c.rfb200_launch_count_reset()
+
+
+def plan_cache_clear() -> None:
+    _c.rfb200_plan_cache_clear()
+
+
+def set_dst_ortho_quirk(enabled: bool) -> None:
+    """True (default): DST-II/III with ortho=True scale element 0 like the reference
+    (README.md:61-65); False: element N-1 like SciPy."""
+    _c.rfb200_set_dst_ortho_quirk(1 if enabled else 0)
+
+
+def set_stream(stream) -> None:
+    """CUDA stream (integer handle) used by the host-array path of this thread;
+    None restores the library's own stream."""
+    if stream is None:
+        _c.rfb200_use_library_stream()
+    else:
+        _c.rfb200_set_stream(C.c_void_p(int(stream)))
+
+
+def _current_stream() -> int:
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_stream().cuda_stream)
+    return 0
+
+
+def _is_host(a) -> bool:
+    return isinstance(a, np.ndarray)
+
+
+_REAL = (np.dtype(np.float32), np.dtype(np.float64))
+_CPLX = (np.dtype(np.complex64), np.dtype(np.complex128))
+
+
+def _check(op, ain, aout):
+    din, dout = _abi.dtype_of(ain), _abi.dtype_of(aout)
+    want_in = _CPLX if op in ("c2c", "c2r") else _REAL
+    want_out = _CPLX if op in ("c2c", "r2c", "c2c_sym") else _REAL
+    if din not in want_in or dout not in want_out:
+        raise TypeError(f"{op}: unsupported dtypes {din} -> {dout}")
+    if (din in (np.dtype(np.float32), np.dtype(np.complex64))) != (dout in (np.dtype(np.float32), np.dtype(np.complex64))):
+        raise TypeError(f"{op}: input and output precision differ ({din} -> {dout})")
+    return 0 if din in (np.dtype(np.float32), np.dtype(np.complex64)) else 1
+
+
+def _device_call(op, ain, aout, axes, mid):
+    prec = _check(op, ain, aout)
+    pin, shp_in, st_in, _, dev_in, k1 = _abi.describe(ain)
+    pout, shp_out, st_out, _, dev_out, k2 = _abi.describe(aout)
+    if len(shp_in) != len(shp_out):
+        raise ValueError("Input and output array must have the same number of dimensions")
+    shape = shp_out if op == "c2r" else shp_in
+    nd = len(shape)
+    ax = [int(a) for a in np.asarray(axes).ravel()]
+    for a in ax:
+        if not 0 <= a < nd:
+            raise ValueError("axis out of range")
+    A = (C.c_int64 * max(nd, 1))
+    shape_c, sin_c, sout_c = A(*shape), A(*st_in), A(*st_out)
+    axes_c = (C.c_uint64 * max(len(ax), 1))(*ax)
+    rc = getattr(_c, "rfb200_" + op)(
+        prec, nd, shape_c, sin_c, sout_c, len(ax), axes_c, *mid, C.c_void_p(pin), C.c_void_p(pout),
+        C.c_void_p(_current_stream()),
+    )
+    if rc != 0:
+        raise TransformError(last_error())
+    return aout
+
+
+def _host_call(op, ain, aout, axes, args):
+    _check(op, ain, aout)
+    getattr(lib, op)(ain, aout, axes, *args)
+    err = last_error()
+    if err:
+        raise TransformError(err)
+    return aout
+
+
+def _call(op, ain, aout, axes, host_args, dev_mid):
+    hi, ho = _is_host(ain), _is_host(aout)
+    if hi != ho:
+        raise TypeError("input and output must both be host arrays or both be device arrays")
+    if hi:
+        return _host_call(op, ain, aout, axes, host_args)
+    return _device_call(op, ain, aout, axes, dev_mid)
+
+
+def c2c(ain, aout, axes, forward, fct, nthreads=1):
+    return _call("c2c", ain, aout, axes, (forward, fct, nthreads), (int(bool(forward)), float(fct)))
+
+
+def r2c(ain, aout, axes, forward, fct, nthreads=1):
+    return _call("r2c", ain, aout, axes, (forward, fct, nthreads), (int(bool(forward)), float(fct)))
+
+
+def c2r(ain, aout, axes, forward, fct, nthreads=1):
+    return _call("c2r", ain, aout, axes, (forward, fct, nthreads), (int(bool(forward)), float(fct)))
+
+
+def c2c_sym(ain, aout, axes, forward, fct, nthreads=1):
+    return _call("c2c_sym", ain, aout, axes, (forward, fct, nthreads), (int(bool(forward)), float(fct)))
+
+
+def dct(ain, aout, axes, type, fct, ortho, nthreads=1):
+    if int(type) not in (1, 2, 3, 4):
+        raise ValueError("invalid DCT type")
+    return _call("dct", ain, aout, axes, (type, fct, ortho, nthreads), (int(type), float(fct), int(bool(ortho))))
+
+
+def dst(ain, aout, axes, type, fct, ortho, nthreads=1):
+    if int(type) not in (1, 2, 3, 4):
+        raise ValueError("invalid DST type")
+    return _call("dst", ain, aout, axes, (type, fct, ortho, nthreads), (int(type), float(fct), int(bool(ortho))))
+
+
+def r2r_separable_hartley(ain, aout, axes, fct, nthreads=1):
+    return _call("r2r_separable_hartley", ain, aout, axes, (fct, nthreads), (float(fct),))
+
+
+def r2r_genuine_hartley(ain, aout, axes, fct, nthreads=1):
+    return _call("r2r_genuine_hartley", ain, aout, axes, (fct, nthreads), (float(fct),))
+
+
+def r2r_fftpack(ain, aout, axes, real2hermitian, forward, fct, nthreads=1):
+    return _call(
+        "r2r_fftpack", ain, aout, axes, (real2hermitian, forward, fct, nthreads),
+        (int(bool(real2hermitian)), int(bool(forward)), float(fct)),
+    )
+
+
+def good_size(n, real):
+    return lib.good_size(n, real)
+
+
+separable_hartley = r2r_separable_hartley
+genuine_hartley = r2r_genuine_hartley
+fftpack = r2r_fftpack

@@ -1,0 +1,363 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI
+of librocketfft_b200.so -- the numba_* symbols with host arrays (H2D/D2H staged inside)
+or the rfb200_* device entry points with torch CUDA tensors -- and is compared with the
+compiled reference (oracle/_ref, when it travelled with the snapshot), the NumPy oracle
+and the committed golden vectors.  Tolerance: rel-L2 <= 1e-5*log2(n) (fp32),
+1e-13*log2(n) (fp64), n = product of the transformed lengths (north-star bound)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import parity
+from oracle import pocketfft_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rocket_fft_b200 as r
+
+    return r
+
+
+def trusted():
+    """The checker: the compiled reference if present, else the NumPy oracle."""
+    ref = parity.reflib()
+    return ref if ref is not None else O
+
+
+def cplx(rng, shape, dt):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dt)
+
+
+CD = {np.float32: np.complex64, np.float64: np.complex128}
+
+
+def check(got, want, dt, n, what=""):
+    e = parity.l2err(got, want)
+    assert e <= parity.tol(dt, n), (what, e, parity.tol(dt, n))
+
+
+# ------------------------------------------------------------------------------------
+def test_golden_vectors(R):
+    d, cases = parity.golden()
+    for i, c in enumerate(cases):
+        ain = d[f"c{i}_in"]
+        want = d[f"c{i}_out"]
+        got = np.zeros_like(want)
+        parity.call(R, c, ain.copy(), got)
+        shape = want.shape if c["op"] == "c2r" else ain.shape
+        n = parity.tlen(c, shape)
+        if c["op"] in ("dct", "dst") and c["type"] == 1:
+            n = 2 * n
+        check(got, want, want.dtype, n, (i, c))
+
+
+def test_readme_example(R):
+    d, _ = parity.golden()
+    out = np.empty(8, dtype=np.complex128)
+    R.c2c(d["readme_in"], out, [0], True, 1.0)
+    check(out, d["readme_out"], np.complex128, 8)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_c2c_every_length_to_600(R, dt):
+    T = trusted()
+    rng = np.random.default_rng(1)
+    cdt = CD[dt]
+    for n in range(1, 601):
+        x = cplx(rng, (3, n), cdt)
+        for fwd in (True, False):
+            a, b = np.empty_like(x), np.empty_like(x)
+            R.c2c(x, a, [1], fwd, 1.0)
+            T.c2c(x, b, [1], fwd, 1.0)
+            check(a, b, dt, n, (n, fwd))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_c2c_selected_lengths(R, dt):
+    T = trusted()
+    rng = np.random.default_rng(2)
+    cdt = CD[dt]
+    lens = [601, 625, 729, 1000, 1021, 1024, 1331, 2011, 2047, 2048, 2187, 4096, 5400, 7776, 8192, 15015, 16384,
+            32768, 65536, 65537, 100003, 3 * 5 * 7 * 11 * 13 * 4, 2**18, 2**20, 1000003, 2000376]
+    for n in lens:
+        rows = 2 if n > 100000 else 5
+        x = cplx(rng, (rows, n), cdt)
+        a, b = np.empty_like(x), np.empty_like(x)
+        R.c2c(x, a, [1], True, 1.0)
+        T.c2c(x, b, [1], True, 1.0)
+        check(a, b, dt, n, n)
+        R.c2c(a, a, [1], False, 1.0 / n)  # in place, backward: round trip
+        check(a, x, dt, n, ("roundtrip", n))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_c2c_shapes_strides_axes(R, dt):
+    T = trusted()
+    rng = np.random.default_rng(3)
+    cdt = CD[dt]
+    for shp in ((10,), (127,), (128, 128), (128, 129), (1, 129), (129, 1), (32, 17, 39), (4, 3, 5, 6)):
+        nd = len(shp)
+        x = cplx(rng, shp, cdt)
+        axes_list = [list(range(nd)), [nd - 1], [0]]
+        if nd >= 2:
+            axes_list += [list(p) for p in itertools.permutations(range(nd))][:6] + [[0, 0], [nd - 1, nd - 1, 0]]
+        for axes in axes_list:
+            n = int(np.prod([shp[a] for a in set(axes)]))
+            a, b = np.empty_like(x), np.empty_like(x)
+            R.c2c(x, a, axes, True, 0.5)
+            T.c2c(x, b, axes, True, 0.5)
+            check(a, b, dt, n, (shp, axes))
+    # views: F-order, reversed, sliced, transposed output
+    base = cplx(rng, (24, 20, 18), cdt)
+    views = [np.asfortranarray(base), base[::-1, :, ::-1], base[::2, ::3, :], base.transpose(2, 0, 1), base[3:, 1:, 2:]]
+    for v in views:
+        for axes in ([0], [1], [2], [0, 1, 2], [2, 0]):
+            n = int(np.prod([v.shape[a] for a in set(axes)]))
+            a = np.empty(v.shape, dtype=cdt)
+            b = np.empty(v.shape, dtype=cdt)
+            R.c2c(v, a, axes, False, 1.0)
+            T.c2c(v, b, axes, False, 1.0)
+            check(a, b, dt, n, (v.strides, axes))
+            af = np.asfortranarray(np.zeros(v.shape, dtype=cdt))
+            R.c2c(v, af, axes, False, 1.0)
+            check(af, b, dt, n, ("F-out", v.strides, axes))
+    # in place
+    x = cplx(rng, (64, 48), cdt)
+    want = np.empty_like(x)
+    T.c2c(x, want, [0, 1], True, 1.0)
+    assert R.c2c(x, x, [0, 1], True, 1.0) is x
+    check(x, want, dt, 64 * 48)
+    # zero-sized dims are a silent no-op
+    z = np.zeros((0, 5), dtype=cdt)
+    R.c2c(z, z, [1], True, 1.0)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_real_transforms_lengths(R, dt):
+    T = trusted()
+    rng = np.random.default_rng(4)
+    cdt = CD[dt]
+    for n in list(range(1, 131)) + [255, 256, 257, 1000, 1021, 2048, 4096, 16384, 30000, 65536, 100003]:
+        x = rng.standard_normal((2, n)).astype(dt)
+        z = cplx(rng, (2, n // 2 + 1), cdt)
+        for fwd in (True, False):
+            a = np.zeros((2, n // 2 + 1), dtype=cdt)
+            b = np.zeros_like(a)
+            R.r2c(x, a, [1], fwd, 1.0)
+            T.r2c(x, b, [1], fwd, 1.0)
+            check(a, b, dt, n, ("r2c", n, fwd))
+            a, b = np.empty_like(x), np.empty_like(x)
+            R.c2r(z, a, [1], fwd, 1.0)
+            T.c2r(z, b, [1], fwd, 1.0)
+            check(a, b, dt, n, ("c2r", n, fwd))
+            a = np.empty((2, n), dtype=cdt)
+            b = np.empty_like(a)
+            R.c2c_sym(x, a, [1], fwd, 1.0)
+            T.c2c_sym(x, b, [1], fwd, 1.0)
+            check(a, b, dt, n, ("c2c_sym", n, fwd))
+            if n > 5000:
+                continue
+            for r2h in (True, False):
+                a, b = np.empty_like(x), np.empty_like(x)
+                R.r2r_fftpack(x, a, [1], r2h, fwd, 1.0)
+                T.r2r_fftpack(x, b, [1], r2h, fwd, 1.0)
+                check(a, b, dt, n, ("fftpack", n, r2h, fwd))
+        a, b = np.empty_like(x), np.empty_like(x)
+        R.r2r_separable_hartley(x, a, [1], 1.0)
+        T.r2r_separable_hartley(x, b, [1], 1.0)
+        check(a, b, dt, n, ("hartley", n))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_real_transforms_nd(R, dt):
+    T = trusted()
+    rng = np.random.default_rng(5)
+    cdt = CD[dt]
+    for shp in ((128, 128), (128, 129), (1, 129), (129, 1), (32, 17, 39), (12, 10, 9)):
+        nd = len(shp)
+        x = rng.standard_normal(shp).astype(dt)
+        for axes in ([list(range(nd)), [nd - 1], [0], [nd - 1, 0], [1, 0]]):
+            n = int(np.prod([shp[a] for a in set(axes)]))
+            oshp = list(shp)
+            oshp[axes[-1]] = shp[axes[-1]] // 2 + 1
+            a = np.zeros(oshp, dtype=cdt)
+            b = np.zeros(oshp, dtype=cdt)
+            R.r2c(x, a, axes, True, 1.0)
+            T.r2c(x, b, axes, True, 1.0)
+            check(a, b, dt, n, ("r2c", shp, axes))
+            zin = cplx(rng, oshp, cdt)
+            a2, b2 = np.empty_like(x), np.empty_like(x)
+            R.c2r(zin, a2, axes, False, 1.0 / n)
+            T.c2r(zin, b2, axes, False, 1.0 / n)
+            check(a2, b2, dt, n, ("c2r", shp, axes))
+            a3 = np.empty(shp, dtype=cdt)
+            b3 = np.empty(shp, dtype=cdt)
+            R.c2c_sym(x, a3, axes, True, 1.0)
+            T.c2c_sym(x, b3, axes, True, 1.0)
+            check(a3, b3, dt, n, ("c2c_sym", shp, axes))
+            a4, b4 = np.empty_like(x), np.empty_like(x)
+            R.r2r_genuine_hartley(x, a4, axes, 1.0)
+            T.r2r_genuine_hartley(x, b4, axes, 1.0)
+            check(a4, b4, dt, n, ("genuine", shp, axes))
+            R.r2r_separable_hartley(x, a4, axes, 1.0)
+            T.r2r_separable_hartley(x, b4, axes, 1.0)
+            check(a4, b4, dt, n, ("separable", shp, axes))
+            R.r2r_fftpack(x, a4, axes, True, True, 1.0)
+            T.r2r_fftpack(x, b4, axes, True, True, 1.0)
+            check(a4, b4, dt, n, ("fftpack", shp, axes))
+    # Hartley identities of the reference's own tests (tests/test_low_level_interface.py:90-167)
+    x = (rng.random((32, 17, 39)) - 0.5).astype(dt)
+    axes = [0, 1, 2]
+    y = np.empty_like(x)
+    R.r2r_genuine_hartley(x, y, axes, 1.0)
+    v = np.fft.fftn(x.astype(np.complex128))
+    check(y, v.real + v.imag, dt, x.size, "genuine == Re+Im fftn")
+    v1 = x.copy()
+    f = 1 / np.sqrt(x.size)
+    assert R.r2r_genuine_hartley(R.r2r_genuine_hartley(v1, v1, axes, f), v1, axes, f) is v1
+    check(v1, x, dt, x.size, "genuine twice in place")
+    y2 = np.empty_like(x)
+    R.r2r_separable_hartley(R.r2r_separable_hartley(x, y, axes, 1.0), y2, axes, 1.0 / x.size)
+    check(y2, x, dt, x.size, "separable twice")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_dct_dst(R, dt):
+    T = trusted()
+    rng = np.random.default_rng(6)
+    for n in list(range(1, 40)) + [64, 100, 101, 128, 255, 256, 1000, 1024, 2048, 4097]:
+        x = rng.standard_normal((3, n)).astype(dt)
+        for kind in ("dct", "dst"):
+            for t in (1, 2, 3, 4):
+                if kind == "dct" and t == 1 and n < 2:
+                    continue
+                for ortho in (False, True):
+                    a, b = np.empty_like(x), np.empty_like(x)
+                    getattr(R, kind)(x, a, [1], t, 1.0, ortho)
+                    getattr(T, kind)(x, b, [1], t, 1.0, ortho)
+                    check(a, b, dt, 2 * n + 2, (kind, t, n, ortho))
+    x = rng.standard_normal((40, 24, 6)).astype(dt)
+    for kind in ("dct", "dst"):
+        for t in (1, 2, 3, 4):
+            for axes in ([0, 1], [2], [1, 0, 2], [0, 0]):
+                a, b = np.empty_like(x), np.empty_like(x)
+                getattr(R, kind)(x, a, axes, t, 0.25, False)
+                getattr(T, kind)(x, b, axes, t, 0.25, False)
+                check(a, b, dt, 4 * x.size, (kind, t, axes))
+    # FFTW known answers (tests/test_scipy_testsuite.py:1192-1293)
+    d, _ = parity.golden()
+    for k in [k for k in d.files if k.startswith("fftw_")]:
+        _, kind, t, N = k.split("_")
+        xx = np.linspace(0, int(N) - 1, int(N)).astype(dt)
+        y = np.empty_like(xx)
+        getattr(R, kind)(xx, y, [0], int(t), 1.0, False)
+        check(y, d[k], dt, 4 * int(N), k)
+
+
+def test_config1_c2c_complex128_4096x4096(R):
+    """BASELINE config 1 at full size."""
+    T = trusted()
+    rng = np.random.default_rng(0)
+    x = cplx(rng, (4096, 4096), np.complex128)
+    a, b = np.empty_like(x), np.empty_like(x)
+    R.c2c(x, a, [1], True, 1.0)
+    T.c2c(x, b, [1], True, 1.0, 8) if T is not O else T.c2c(x, b, [1], True, 1.0)
+    check(a, b, np.float64, 4096, "cfg1")
+
+
+def test_config4_nonpow2_and_bluestein(R):
+    T = trusted()
+    rng = np.random.default_rng(3)
+    x = cplx(rng, (256, 15015), np.complex64)
+    a, b = np.empty_like(x), np.empty_like(x)
+    R.c2c(x, a, [1], True, 1.0)
+    T.c2c(x, b, [1], True, 1.0)
+    check(a, b, np.float32, 15015, "cfg4a")
+    x = cplx(rng, (8, 1000003), np.complex64)
+    a, b = np.empty_like(x), np.empty_like(x)
+    R.c2c(x, a, [1], True, 1.0)
+    T.c2c(x, b, [1], True, 1.0)
+    check(a, b, np.float32, 1000003, "cfg4b")
+
+
+def test_config2_reduced_and_config5_reduced(R):
+    T = trusted()
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2048, 2048)).astype(np.float32)
+    a = np.zeros((2048, 1025), dtype=np.complex64)
+    b = np.zeros_like(a)
+    R.r2c(x, a, [0, 1], True, 1.0)
+    T.r2c(x, b, [0, 1], True, 1.0)
+    check(a, b, np.float32, 2048 * 2048, "cfg2 r2c")
+    y, y2 = np.empty_like(x), np.empty_like(x)
+    R.c2r(a, y, [0, 1], False, 1.0 / x.size)
+    check(y, x, np.float32, 2048 * 2048, "cfg2 roundtrip")
+    x = rng.standard_normal((256, 256, 64))
+    for kind in ("dct", "dst"):
+        a, b = np.empty_like(x), np.empty_like(x)
+        getattr(R, kind)(x, a, [0, 1], 2, 1.0, False)
+        getattr(T, kind)(x, b, [0, 1], 2, 1.0, False)
+        check(a, b, np.float64, 4 * 256 * 256, "cfg5 " + kind)
+
+
+def test_device_arrays_and_full_size_properties(R):
+    """rfb200_* entry points on torch CUDA tensors; full-size configs through
+    size-independent properties (round trip, linearity, Parseval)."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(0)
+    # device path equals host path
+    x = torch.randn(64, 1000, dtype=torch.complex128, device=dev, generator=g)
+    y = torch.empty_like(x)
+    R.c2c(x, y, [1], True, 1.0)
+    torch.cuda.synchronize()
+    xh = x.cpu().numpy()
+    yh = np.empty_like(xh)
+    R.c2c(xh, yh, [1], True, 1.0)
+    assert parity.l2err(y.cpu().numpy(), yh) < 1e-15
+    # config 2 full size: rfft2 -> irfft2 round trip, Parseval
+    x = torch.randn(16384, 16384, dtype=torch.float32, device=dev, generator=g)
+    X = torch.empty(16384, 8193, dtype=torch.complex64, device=dev)
+    R.r2c(x, X, [0, 1], True, 1.0)
+    e_time = float((x.double() ** 2).sum())
+    w = torch.full((8193,), 2.0, dtype=torch.float64, device=dev)
+    w[0] = 1.0
+    w[-1] = 1.0
+    e_freq = float(((X.real.double() ** 2 + X.imag.double() ** 2) * w).sum()) / x.numel()
+    assert abs(e_freq - e_time) / e_time < 1e-5
+    xr = torch.empty_like(x)
+    R.c2r(X, xr, [0, 1], False, 1.0 / x.numel())
+    err = float(torch.linalg.vector_norm((xr - x).double()) / torch.linalg.vector_norm(x.double()))
+    assert err < parity.tol(np.float32, 2**28), err
+    # spot rows against torch.fft (cuFFT) as a side check
+    ref = torch.fft.rfft2(x[:, :])[:8]
+    err = float(torch.linalg.vector_norm((X[:8] - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
+    assert err < parity.tol(np.float32, 2**28), err
+    del x, X, xr, ref
+    # config 3 at 256^3 (+ linearity), full 1024^3 round trip if memory allows
+    v = torch.randn(256, 256, 256, dtype=torch.complex64, device=dev, generator=g)
+    V = torch.empty_like(v)
+    R.c2c(v, V, [0, 1, 2], True, 1.0)
+    ref = torch.fft.fftn(v)
+    err = float(torch.linalg.vector_norm((V - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
+    assert err < parity.tol(np.float32, 2**24), err
+    del v, V, ref
+    v = torch.randn(1024, 1024, 1024, dtype=torch.complex64, device=dev, generator=g)
+    V = torch.empty_like(v)
+    R.c2c(v, V, [0, 1, 2], True, 1.0)
+    R.c2c(V, V, [0, 1, 2], False, 1.0 / v.numel())
+    err = float(torch.linalg.vector_norm((V - v)[:64].to(torch.complex128)) / torch.linalg.vector_norm(v[:64].to(torch.complex128)))
+    assert err < parity.tol(np.float32, 2**30), err
+    del v, V
+    # config 5 full size: dct-II then dct-III inverts up to 1/(2N)^2
+    x = torch.randn(2048, 2048, 64, dtype=torch.float64, device=dev, generator=g)
+    y = torch.empty_like(x)
+    R.dct(x, y, [0, 1], 2, 1.0, False)
+    R.dct(y, y, [0, 1], 3, 1.0 / (4096.0 * 4096.0), False)
+    err = float(torch.linalg.vector_norm(y - x) / torch.linalg.vector_norm(x))
+    assert err < parity.tol(np.float64, 4096 * 4096), err

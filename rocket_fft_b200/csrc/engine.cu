@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "geom_fill.cuh"
 #include "tile_kernel.cuh"
 
 namespace rfb {
@@ -264,9 +265,8 @@ static bool plan_tile(const LineJob &job, const std::vector<Dim> &dims, TilePlan
 template <typename T, bool ALIGNED>
 static void launch_tile_typed(const LineJob &job, const std::vector<Dim> &dims, const TilePlan &tp, cudaStream_t s) {
     TileGeom<T> g;
-    memset(&g, 0, sizeof(g));
+    const uint64_t ntiles = fill_geom<T>(g, job, dims, tp.W, tp.load_lf, tp.store_lf);
     const uint32_t n = (uint32_t)job.n;
-    g.n = n;
     g.npass = (uint32_t)tp.sched.size();
     uint32_t l1 = 1;
     for (uint32_t i = 0; i < g.npass; ++i) {
@@ -279,50 +279,9 @@ static void launch_tile_typed(const LineJob &job, const std::vector<Dim> &dims, 
         ps.d_R = make_fastdiv(ps.R);
         l1 *= ps.R;
     }
-    g.W = tp.W;
     g.pitch = tp.pitch;
     g.padsh = tp.padsh;
-    g.d_n = make_fastdiv(n);
-    g.d_W = make_fastdiv(tp.W);
-    g.load_line_fast = tp.load_lf ? 1 : 0;
-    g.store_line_fast = tp.store_lf ? 1 : 0;
-    g.load_mode = job.load_mode;
-    g.store_mode = job.store_mode;
-    g.flags = job.flags;
-    g.n_in = (uint32_t)(job.n_in ? job.n_in : job.n);
-    g.n_out = (job.store_mode == ST_HALF) ? n / 2 + 1 : n;
-    g.d_nout = make_fastdiv(g.n_out);
-    g.backward = job.backward ? 1 : 0;
-    g.in_sa = job.is;
-    g.out_sa = job.os;
-    g.tw_dim = -1;
-    for (int d = 0; d < MAXB; ++d) {
-        if (d < (int)dims.size()) {
-            g.bext[d] = (uint32_t)dims[d].n;
-            g.in_bs[d] = dims[d].is;
-            g.out_bs[d] = dims[d].os;
-            if (dims[d].tw && job.twN) g.tw_dim = d;
-        } else {
-            g.bext[d] = 1;
-            g.in_bs[d] = 0;
-            g.out_bs[d] = 0;
-        }
-    }
-    const uint32_t tiles0 = (g.bext[0] + tp.W - 1) / tp.W;
-    g.d_t0 = make_fastdiv(tiles0);
-    g.d_e1 = make_fastdiv(g.bext[1]);
-    const uint64_t ntiles = (uint64_t)tiles0 * g.bext[1] * g.bext[2];
-    if (ntiles >= (1ull << 31)) { set_error("too many tiles in one launch"); throw Error(); }
-    g.in = job.in;
-    g.out = job.out;
     g.tw = (n > 1) ? (const cx<T> *)get_table(TAB_LINE, job.prec, n, 0) : nullptr;
-    g.fct = (T)job.fct;
-    if (g.tw_dim >= 0) {
-        const uint32_t S = split_size(job.twN);
-        g.d_twS = make_fastdiv(S);
-        g.twA = (const cx<T> *)get_table(TAB_SPLIT_A, job.prec, job.twN, S);
-        g.twB = (const cx<T> *)get_table(TAB_SPLIT_B, job.prec, job.twN, S);
-    }
     auto kern = fft_tile_kernel<T, ALIGNED>;
     static thread_local int dev_set = -1;
     int dev = 0;
@@ -336,19 +295,6 @@ static void launch_tile_typed(const LineJob &job, const std::vector<Dim> &dims, 
 }
 
 static void launch_tile(const LineJob &job, const std::vector<Dim> &dims, const TilePlan &tp, cudaStream_t s) {
-    // more batch dims than one launch takes: peel the outermost ones on the host
-    if (dims.size() > (size_t)MAXB) {
-        std::vector<Dim> inner(dims.begin(), dims.end() - 1);
-        const Dim &o = dims.back();
-        if (o.tw && job.twN) { set_error("internal: four-step dim peeled"); throw Error(); }
-        for (int64_t i = 0; i < o.n; ++i) {
-            LineJob sub = job;
-            sub.in = job.in + i * o.is;
-            sub.out = job.out + i * o.os;
-            launch_tile(sub, inner, tp, s);
-        }
-        return;
-    }
     const bool al = alignment_ok(job, dims);
     if (job.prec) {
         if (al) launch_tile_typed<double, true>(job, dims, tp, s);
@@ -383,6 +329,7 @@ static std::vector<Dim> contiguous_batch(const std::vector<Dim> &b, uint64_t lin
 static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 static void run_via_scratch(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 
 static bool choose_split(uint64_t n, int prec, uint64_t &n1, uint64_t &n2) {
     // divisor pair closest to sqrt(n) whose members both factor into radices <= RMAX_GENERIC
@@ -431,9 +378,36 @@ void run_lines(const LineJob &job_in, cudaStream_t s) {
     });
     if (total_lines(dims) >= (1ull << 31)) { set_error("too many lines"); throw Error(); }
 
+    run_norm(job, dims, s);
+}
+
+// dims: extent > 1, sorted by stride (dims[0] = the tile dim)
+static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    // more batch dims than one launch takes: peel the outermost ones on the host
+    if (dims.size() > (size_t)MAXB) {
+        std::vector<Dim> inner(dims.begin(), dims.end() - 1);
+        const Dim &o = dims.back();
+        if (o.tw && job.twN) { set_error("internal: four-step dim peeled"); throw Error(); }
+        for (int64_t i = 0; i < o.n; ++i) {
+            LineJob sub = job;
+            sub.in = job.in + i * o.is;
+            sub.out = job.out + i * o.os;
+            run_norm(sub, inner, s);
+        }
+        return;
+    }
     const bool simple = (job.load_mode == LD_C2C || job.load_mode == LD_REAL) && job.store_mode == ST_C2C &&
                         job.flags == 0 && (job.n_in == 0 || job.n_in == job.n);
     const size_t esz = job.prec ? 16 : 8;
+    // power-of-two lines: register-resident Stockham kernel
+    static const bool use_pow2 = env_int("RFB200_NO_POW2", 0) == 0;
+    if (use_pow2 && alignment_ok(job, dims)) {
+        const bool load_lf = !dims.empty() && iabs64(dims[0].is) < iabs64(job.is);
+        const bool store_lf = !dims.empty() && iabs64(dims[0].os) < iabs64(job.os);
+        const bool done = job.prec ? launch_pow2_f64(job, dims, load_lf, store_lf, s)
+                                   : launch_pow2_f32(job, dims, load_lf, store_lf, s);
+        if (done) return;
+    }
     TilePlan tp;
     bool tile_ok = plan_tile(job, dims, tp);
     if (tile_ok && simple && (tp.load_lf || tp.store_lf) && job.twN == 0) {
@@ -497,21 +471,36 @@ static void run_via_scratch(const LineJob &job, const std::vector<Dim> &dims, cu
 }
 
 static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
-    const size_t esz = job.prec ? 16 : 8;
+    const int64_t esz = job.prec ? 16 : 8;
     uint64_t n1, n2;
     choose_split(job.n, job.prec, n1, n2);
     const uint64_t L = total_lines(dims);
-    Scratch sc(L * job.n * esz, s);
+    Scratch sc(L * job.n * (uint64_t)esz, s);
+    // Scratch layout: when the lines are strided (neighbouring lines adjacent in memory) the
+    // scratch keeps that neighbour dim fastest, [..][n][dim0], so that both steps read and write
+    // rows of adjacent lines; contiguous lines use [..][dim0][n].
+    const bool lf = !dims.empty() && (iabs64(dims[0].is) < iabs64(job.is) || iabs64(dims[0].os) < iabs64(job.os));
+    std::vector<int64_t> sstr(dims.size());
+    int64_t s_axis, acc;
+    if (lf) {
+        sstr[0] = esz;
+        s_axis = dims[0].n * esz;
+        acc = s_axis * (int64_t)job.n;
+        for (size_t i = 1; i < dims.size(); ++i) { sstr[i] = acc; acc *= dims[i].n; }
+    } else {
+        s_axis = esz;
+        acc = (int64_t)job.n * esz;
+        for (size_t i = 0; i < dims.size(); ++i) { sstr[i] = acc; acc *= dims[i].n; }
+    }
     // A: for every residue j0 (mod n2) an n1-point DFT over j1 of x[j1*n2 + j0], times
     //    exp(-2 pi i j0 k1 / n), stored at scratch[k1*n2 + j0]
     LineJob A;
     A.prec = job.prec;
     A.n = n1;
     A.is = (int64_t)n2 * job.is;
-    A.os = (int64_t)(n2 * esz);
-    A.batch = contiguous_batch(dims, job.n * esz, false);
-    for (auto &d : A.batch) d.tw = false;
-    A.batch.push_back(Dim{(int64_t)n2, job.is, (int64_t)esz, true});
+    A.os = (int64_t)n2 * s_axis;
+    for (size_t i = 0; i < dims.size(); ++i) A.batch.push_back(Dim{dims[i].n, dims[i].is, sstr[i], false});
+    A.batch.push_back(Dim{(int64_t)n2, job.is, s_axis, true});
     A.in = job.in;
     A.out = (char *)sc.p;
     A.backward = job.backward;
@@ -523,11 +512,10 @@ static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaS
     LineJob B;
     B.prec = job.prec;
     B.n = n2;
-    B.is = (int64_t)esz;
+    B.is = s_axis;
     B.os = (int64_t)n1 * job.os;
-    B.batch = contiguous_batch(dims, job.n * esz, true);
-    for (auto &d : B.batch) d.tw = false;
-    B.batch.push_back(Dim{(int64_t)n1, (int64_t)(n2 * esz), job.os, false});
+    for (size_t i = 0; i < dims.size(); ++i) B.batch.push_back(Dim{dims[i].n, sstr[i], dims[i].os, false});
+    B.batch.push_back(Dim{(int64_t)n1, (int64_t)n2 * s_axis, job.os, false});
     B.in = (const char *)sc.p;
     B.out = job.out;
     B.backward = job.backward;

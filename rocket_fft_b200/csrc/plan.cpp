@@ -167,6 +167,33 @@ void fill(std::vector<T> &h, TableKind kind, uint64_t n, uint64_t param, size_t 
         h[2 * t + 1] = (T)(-s);
     }
 }
+// Pass-major, q-major twiddles of the register-resident power-of-two kernel: pass p with
+// radix R_p and inner stride ido_p > 1 owns (R_p-1)*ido_p entries exp(-2 pi i i q/(R_p ido_p))
+// stored at [(q-1)*ido_p + i].  Pass structure as in P2<LOGN> (pow2_kernel.cuh): one radix
+// 2/4/8 pass first when log2 n is not a multiple of 4, then radix-16 passes.
+template <typename T>
+void fill_stockham(std::vector<T> &h, uint64_t n) {
+    int logn = 0;
+    while ((1ull << logn) < n) ++logn;
+    std::vector<uint32_t> rad;
+    if (logn % 4) rad.push_back(1u << (logn % 4));
+    for (int i = 0; i < logn / 4; ++i) rad.push_back(16);
+    h.clear();
+    uint64_t l1 = 1;
+    for (auto R : rad) {
+        const uint64_t ido = n / (l1 * R);
+        if (ido > 1)
+            for (uint32_t q = 1; q < R; ++q)
+                for (uint64_t i = 0; i < ido; ++i) {
+                    long double c, s;
+                    sincos_2pi(i * q, R * ido, c, s);
+                    h.push_back((T)c);
+                    h.push_back((T)(-s));
+                }
+        l1 *= R;
+    }
+    if (h.empty()) { h.push_back(T(1)); h.push_back(T(0)); }
+}
 }  // namespace
 
 const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool *created, void **writable) {
@@ -188,11 +215,22 @@ const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool
         case TAB_CHIRP: count = n; break;
         case TAB_CHIRP_FFT: count = param; break;
         case TAB_QUARTER: count = n + 1; break;
+        case TAB_STOCKHAM: count = n; break;  // upper bound: sum (R-1)*ido < n
     }
     size_t esz = prec ? 16 : 8;
     void *d = nullptr;
     RFB_CUDA_CHECK(cudaMalloc(&d, count * esz > 0 ? count * esz : esz));
-    if (kind != TAB_CHIRP_FFT) {
+    if (kind == TAB_STOCKHAM) {
+        if (prec) {
+            std::vector<double> h;
+            fill_stockham(h, n);
+            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<float> h;
+            fill_stockham(h, n);
+            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    } else if (kind != TAB_CHIRP_FFT) {
         if (prec) {
             std::vector<double> h;
             fill(h, kind, n, param, count);

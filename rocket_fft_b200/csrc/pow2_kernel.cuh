@@ -1,0 +1,269 @@
+// Register-resident Stockham kernel for power-of-two lines, 16 <= N <= 16384.
+//
+// A CTA owns W lines; every thread keeps 16 points of one line in registers through all
+// passes (radix-16 butterflies, preceded by one radix-2/4/8 pass when log2 N is not a
+// multiple of 4).  The first pass reads global memory directly into registers, the last
+// pass writes registers directly to global memory -- both fully coalesced, because in the
+// autosort formulation thread t touches t + m*N/R -- and between two passes the data makes
+// exactly one trip through shared memory, laid out so that the writer (contiguous) and the
+// reader (stride ido*R between neighbouring butterflies) are both bank-conflict free.
+// Twiddles come from a per-length table stored pass-major/q-major so that the 32 lanes of a
+// warp read consecutive entries.
+//
+// MODE 1 fuses the even-length real transform: the n = 2N real line is read as N complex
+// points, transformed, and the Hermitian unpack (one extra trip through shared memory) writes
+// bins 0..N.  (Counterpart of rfftp + general_r2c in the reference,
+// _pocketfft_hdronly.h:1836-2717, 3723-3779; different algorithm.)
+#pragma once
+#include "common.cuh"
+#include "line_io.cuh"
+#include "radix.cuh"
+#include "tile_kernel.cuh"
+
+namespace rfb {
+
+template <int LOGN>
+struct P2 {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int REM = LOGN % 4;
+    static constexpr int NP16 = LOGN / 4;
+    static constexpr int RT = 1 << REM;  // small radix, executed first (1: none)
+    static constexpr int NPASS = NP16 + (REM ? 1 : 0);
+    static constexpr int TPL = N / 16;   // threads per line
+    __host__ __device__ static constexpr int radix(int p) { return (REM && p == 0) ? RT : 16; }
+    __host__ __device__ static constexpr int l1(int p) {
+        int l = 1;
+        for (int i = 0; i < p; ++i) l *= radix(i);
+        return l;
+    }
+    __host__ __device__ static constexpr int ido(int p) { return N / (l1(p) * radix(p)); }
+    __host__ __device__ static constexpr int twoff(int p) {
+        int o = 0;
+        for (int i = 0; i < p; ++i) o += (radix(i) - 1) * ido(i);
+        return o;
+    }
+    static constexpr int PAD = N / 16;
+};
+
+// shared-memory slot of logical element a in the exchange that FEEDS pass P
+template <int LOGN, int P>
+__device__ __forceinline__ int p2_phys(int a) {
+    constexpr int ido = P2<LOGN>::ido(P), R = P2<LOGN>::radix(P);
+    if constexpr (ido < 16) return a + ido * (a / (ido * R));
+    else return a;
+}
+
+template <typename T, int LOGN, int W, int MODE>
+struct Pow2Body {
+    using C = cx<T>;
+    using PL = P2<LOGN>;
+    static constexpr int N = PL::N, TPL = PL::TPL, NT = W * TPL;
+    static constexpr int PITCH = (W == 1) ? (N + PL::PAD) : ((N + PL::PAD) | 1);
+
+    static __device__ __forceinline__ void map(bool lf, int tid, int &w, int &t) {
+        if (lf) { w = tid % W; t = tid / W; }
+        else { w = tid / TPL; t = tid % TPL; }
+    }
+
+    // butterflies + twiddles of pass P on the 16 registers
+    template <int P>
+    static __device__ __forceinline__ void compute(C *v, int t, const C *__restrict__ stw) {
+        constexpr int R = PL::radix(P), NB = 16 / R, ido = PL::ido(P);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) Dft<T, R>::run(v + j * R);
+        if constexpr (ido > 1) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int i = (t + j * TPL) % ido;
+                const C *tw = stw + PL::twoff(P) + i;
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[j * R + q] = cmul(v[j * R + q], __ldg(tw + (q - 1) * ido));
+            }
+        }
+    }
+
+    // registers (outputs of pass P-1) -> shared -> registers (inputs of pass P)
+    template <int P>
+    static __device__ __forceinline__ void exchange(C *v, C *buf, int tid, bool lf_prev, bool lf_next, bool first) {
+        constexpr int Rp = PL::radix(P - 1), NBp = 16 / Rp;
+        constexpr int ido = PL::ido(P);
+        int w, t;
+        map(lf_prev, tid, w, t);
+        if (!first) __syncthreads();
+        C *line = buf + w * PITCH;
+#pragma unroll
+        for (int j = 0; j < NBp; ++j)
+#pragma unroll
+            for (int q = 0; q < Rp; ++q) line[p2_phys<LOGN, P>(t + j * TPL + q * (N / Rp))] = v[j * Rp + q];
+        __syncthreads();
+        map(lf_next, tid, w, t);
+        line = buf + w * PITCH;
+        const int i = t % ido, k = t / ido;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = line[p2_phys<LOGN, P>(i + ido * (m + 16 * k))];
+    }
+
+    static __device__ __forceinline__ void run(const TileGeom<T> &g, const C *__restrict__ stw, C *buf) {
+        uint32_t t0, i1, i2, rest;
+        fdivmod(blockIdx.x, g.d_t0, rest, t0);
+        fdivmod(rest, g.d_e1, i2, i1);
+        const uint32_t w_first = t0 * W;
+        const int wvalid = (int)min((uint32_t)W, g.bext[0] - w_first);
+        const int64_t in_base = (int64_t)w_first * g.in_bs[0] + (int64_t)i1 * g.in_bs[1] + (int64_t)i2 * g.in_bs[2];
+        const int64_t out_base = (int64_t)w_first * g.out_bs[0] + (int64_t)i1 * g.out_bs[1] + (int64_t)i2 * g.out_bs[2];
+        const int tid = threadIdx.x;
+        const bool lf_in = g.load_line_fast != 0, lf_out = g.store_line_fast != 0;
+        C v[16];
+
+        // ---- pass 0: global -> registers -------------------------------------------------
+        {
+            constexpr int R = PL::radix(0), NB = 16 / R, ido = PL::ido(0);
+            int w, t;
+            map(lf_in, tid, w, t);
+            const bool wok = w < wvalid;
+            const char *line = g.in + in_base + (int64_t)w * g.in_bs[0];
+            // All 16 loads are issued back to back with nothing depending on them in between
+            // (memory-level parallelism: 16 independent requests per thread in flight).
+            const bool packed_vec = (MODE == 1) && g.in_sa == (int64_t)sizeof(T);
+            const bool plain = (MODE == 0) && g.load_mode == LD_C2C && g.n_in == (uint32_t)N;
+            if (packed_vec || plain) {
+                const int64_t sa = packed_vec ? (int64_t)(2 * sizeof(T)) : g.in_sa;
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const int e = t + j * TPL + m * ido;
+                        v[j * R + m] = wok ? *reinterpret_cast<const C *>(line + (int64_t)e * sa) : mk<T>(T(0), T(0));
+                    }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const uint32_t e = (uint32_t)(t + j * TPL + m * ido);
+                        C val = mk<T>(T(0), T(0));
+                        if (wok) {
+                            if (MODE == 1) {
+                                val.x = *reinterpret_cast<const T *>(line + (int64_t)(2 * e) * g.in_sa);
+                                val.y = *reinterpret_cast<const T *>(line + (int64_t)(2 * e + 1) * g.in_sa);
+                            } else val = load_value<T, true>(g.load_mode, g.flags, line, g.in_sa, e, (uint32_t)N, g.n_in);
+                        }
+                        v[j * R + m] = val;
+                    }
+            }
+            if (MODE == 0 && g.backward) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = cswap(v[i]);
+            }
+            compute<0>(v, t, stw);
+        }
+        bool first = true;
+        if constexpr (PL::NPASS > 1) {
+            exchange<1>(v, buf, tid, lf_in, lf_out, first);
+            first = false;
+            int w, t;
+            map(lf_out, tid, w, t);
+            compute<1>(v, t, stw);
+        }
+        if constexpr (PL::NPASS > 2) {
+            exchange<2>(v, buf, tid, lf_out, lf_out, first);
+            int w, t;
+            map(lf_out, tid, w, t);
+            compute<2>(v, t, stw);
+        }
+        if constexpr (PL::NPASS > 3) {
+            exchange<3>(v, buf, tid, lf_out, lf_out, first);
+            int w, t;
+            map(lf_out, tid, w, t);
+            compute<3>(v, t, stw);
+        }
+
+        // ---- after the last pass thread t holds bins t + q*N/R --------------------------------
+        constexpr int RL = PL::radix(PL::NPASS - 1), NBL = 16 / RL;
+        int w, t;
+        map(PL::NPASS > 1 ? lf_out : lf_in, tid, w, t);
+        if (MODE == 0) {
+            if (w >= wvalid) return;
+            char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
+            if (g.store_mode == ST_C2C && g.tw_dim < 0) {
+                const T f = g.fct;
+                const bool bw = g.backward != 0;
+#pragma unroll
+                for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                    for (int q = 0; q < RL; ++q) {
+                        const int k = t + j * TPL + q * (N / RL);
+                        C val = cscale(v[j * RL + q], f);
+                        if (bw) val = cswap(val);
+                        *reinterpret_cast<C *>(line + (int64_t)k * g.out_sa) = val;
+                    }
+                return;
+            }
+#pragma unroll
+            for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const uint32_t k = (uint32_t)(t + j * TPL + q * (N / RL));
+                    C val = v[j * RL + q];
+                    if (g.store_mode == ST_HALF && 2 * k > (uint32_t)N) continue;
+                    if (g.tw_dim >= 0) {
+                        const uint32_t c = (g.tw_dim == 0) ? (w_first + w) : (g.tw_dim == 1 ? i1 : i2);
+                        uint32_t hi, lo;
+                        fdivmod(c * k, g.d_twS, hi, lo);
+                        val = cmul(val, cmul(__ldg(g.twA + hi), __ldg(g.twB + lo)));
+                    }
+                    val = cscale(val, g.fct);
+                    if (g.backward) val = cswap(val);
+                    store_value<T, true>(g.store_mode, g.flags, line, g.out_sa, k, val);
+                }
+        } else {
+            // ---- Hermitian unpack of the packed real transform --------------------------------
+            // Z = DFT_N(x[2j] + i x[2j+1]);  X[k] = E + O, X[N-k] = conj(E - O) with
+            // E = (Z[k] + conj Z[N-k])/2, O = -i w^k (Z[k] - conj Z[N-k])/2, w = exp(-2 pi i/(2N))
+            if (!first) __syncthreads();
+            C *sl = buf + w * PITCH;
+#pragma unroll
+            for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                for (int q = 0; q < RL; ++q) sl[t + j * TPL + q * (N / RL)] = v[j * RL + q];
+            __syncthreads();
+            if (w >= wvalid) return;
+            char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
+            const T half = T(0.5) * g.fct;
+            const bool conj_out = g.backward != 0;
+            auto emit = [&](int k) {
+                const C a = sl[k];
+                const C bz = sl[(N - k) & (N - 1)];
+                const C b = mk<T>(bz.x, -bz.y);
+                const C e = mk<T>((a.x + b.x) * half, (a.y + b.y) * half);
+                const C d = mk<T>((a.x - b.x) * half, (a.y - b.y) * half);
+                const C wk = __ldg(g.twA + k);
+                // o = -i * wk * d
+                const C wd = cmul(wk, d);
+                const C o = mk<T>(wd.y, -wd.x);
+                C x0 = mk<T>(e.x + o.x, e.y + o.y);
+                C x1 = mk<T>(e.x - o.x, -(e.y - o.y));
+                if (conj_out) { x0.y = -x0.y; x1.y = -x1.y; }
+                st_cx<T, true>(line + (int64_t)k * g.out_sa, x0);
+                st_cx<T, true>(line + (int64_t)(N - k) * g.out_sa, x1);
+            };
+#pragma unroll
+            for (int j = 0; j < 8; ++j) emit(t + j * TPL);
+            if (t == 0) emit(N / 2);
+        }
+    }
+};
+
+// occupancy target: 1024 threads/SM for float (<= 64 registers), 512 for double (<= 128)
+template <typename T, int NT>
+constexpr int p2_min_blocks() {
+    return (sizeof(T) == 8 ? 512 : 1024) / NT > 0 ? (sizeof(T) == 8 ? 512 : 1024) / NT : 1;
+}
+
+template <typename T, int LOGN, int W, int MODE>
+__global__ void __launch_bounds__(W *(1 << LOGN) / 16, p2_min_blocks<T, W *(1 << LOGN) / 16>()) fft_pow2_kernel(const TileGeom<T> g, const cx<T> *__restrict__ stw) {
+    extern __shared__ __align__(16) unsigned char smem_raw_p2[];
+    Pow2Body<T, LOGN, W, MODE>::run(g, stw, reinterpret_cast<cx<T> *>(smem_raw_p2));
+}
+
+}  // namespace rfb

@@ -1,0 +1,93 @@
+// Dispatch of a line job onto the instantiations of fft_pow2_kernel (one translation unit per
+// precision, see pow2_launch_f32.cu / pow2_launch_f64.cu).
+#pragma once
+#include "geom_fill.cuh"
+#include "pow2_kernel.cuh"
+
+namespace rfb {
+
+// lines per CTA: element-fast tiles aim at 256 threads, line-fast tiles at >= 128-byte rows
+constexpr int p2_we(int logn) { return logn <= 10 ? (256 >> (logn - 4)) : (logn == 11 ? 2 : 1); }
+constexpr int p2_wl(int logn, bool dbl) {
+    return logn <= 8 ? p2_we(logn) : (logn == 9 ? 16 : (logn == 10 ? 8 : (logn == 11 ? 4 : 0)));
+}
+
+template <typename T, int LOGN, int W, int MODE>
+void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s) {
+    using Body = Pow2Body<T, LOGN, W, MODE>;
+    TileGeom<T> g;
+    LineJob j2 = job;
+    if (MODE == 1) j2.n = job.n / 2;  // geometry in complex points
+    const uint64_t ntiles = fill_geom<T>(g, j2, dims, (uint32_t)W, load_lf, store_lf);
+    if (MODE == 1) {
+        g.n_out = (uint32_t)(job.n / 2 + 1);
+        g.twA = (const cx<T> *)get_table(TAB_LINE, job.prec, job.n, 0);
+    }
+    const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
+    const size_t smem = (size_t)W * Body::PITCH * sizeof(cx<T>);
+    auto kern = fft_pow2_kernel<T, LOGN, W, MODE>;
+    static thread_local int dev_set = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_set != dev) {
+        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dev_set = dev;
+    }
+    kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
+    count_launch();
+    RFB_CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T, int LOGN>
+bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, int mode,
+                      cudaStream_t s) {
+    constexpr bool dbl = sizeof(T) == 8;
+    constexpr int WE = p2_we(LOGN), WL = p2_wl(LOGN, dbl);
+    const bool lf = load_lf || store_lf;
+    if (mode == 1) {
+        if (lf) return false;
+        launch_pow2_inst<T, LOGN, WE, 1>(job, dims, load_lf, store_lf, s);
+        return true;
+    }
+    if (!lf) {
+        launch_pow2_inst<T, LOGN, WE, 0>(job, dims, load_lf, store_lf, s);
+        return true;
+    }
+    if constexpr (WL == 0) return false;
+    else {
+        launch_pow2_inst<T, LOGN, WL, 0>(job, dims, load_lf, store_lf, s);
+        return true;
+    }
+}
+
+template <typename T, int MAXLOG>
+bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s) {
+    if (dims.size() > (size_t)MAXB) return false;
+    // which flavour?
+    int mode = 0;
+    uint64_t n = job.n;
+    const bool plain_in = job.n_in == 0 || job.n_in == job.n;
+    if (job.load_mode == LD_REAL && job.store_mode == ST_HALF && job.flags == 0 && plain_in && job.twN == 0 &&
+        (n % 2 == 0) && !load_lf && !store_lf && n >= 32) {
+        // the packed load reads two reals as one complex value: needs complex alignment
+        const uint64_t csz = 2 * sizeof(T);
+        bool al = ((uint64_t)(uintptr_t)job.in % csz) == 0;
+        for (auto &d : dims) al = al && (d.is % (int64_t)csz) == 0;
+        if (!al && job.is == (int64_t)sizeof(T)) return false;
+        mode = 1;
+        n /= 2;
+    } else if (job.store_mode == ST_HC) return false;
+    if (n < 16 || (n & (n - 1))) return false;
+    int logn = 0;
+    while ((1ull << logn) < n) ++logn;
+    if (logn > MAXLOG) return false;
+    switch (logn) {
+#define RFB_P2_CASE(L) case L: if constexpr (L <= MAXLOG) return launch_pow2_logn<T, L>(job, dims, load_lf, store_lf, mode, s); else return false;
+        RFB_P2_CASE(4) RFB_P2_CASE(5) RFB_P2_CASE(6) RFB_P2_CASE(7) RFB_P2_CASE(8) RFB_P2_CASE(9) RFB_P2_CASE(10)
+        RFB_P2_CASE(11) RFB_P2_CASE(12) RFB_P2_CASE(13) RFB_P2_CASE(14)
+#undef RFB_P2_CASE
+    }
+    return false;
+}
+
+}  // namespace rfb

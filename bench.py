@@ -252,12 +252,23 @@ def main():
         ]
         peak, peak_src = load_peaks()
         # dominant kernel: the stage with the larger per-launch time
-        per_launch = [(t_row / max(row_launches, 1), row_bytes, "fft_tile_kernel<float> r2c rows", row_launches),
-                      (t_col / max(col_launches, 1), col_bytes, "fft_tile_kernel<float> four-step column pass", col_launches)]
+        per_launch = [(t_row / max(row_launches, 1), row_bytes, "fft_pow2_kernel<float,13,1,1> r2c rows", row_launches),
+                      (t_col / max(col_launches, 1), col_bytes, "fft_pow2_kernel<float,7,32,0> four-step column pass", col_launches)]
         dom = max(per_launch, key=lambda p: p[0])
         achieved = dom[1] / (dom[0] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel for ONE image, from the
+        # committed `ncu --set full` capture (profiles/r01_ncu_rows_kernel.txt); x images per launch
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                key = "rows" if dom[2].endswith("r2c rows") else "cols_pass"
+                traffic = tj[key]["dram_bytes_per_image"] * B
+            except Exception:
+                traffic = None
         roofline = {"bound": "hbm", "kernel": dom[2], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[0],
                     "whole_step_frac_of_compulsory": (B * alg_bytes_per_image() / (ms_per_step * 1e-3) / 1e9) / peak}
 
@@ -284,6 +295,8 @@ def main():
                "d2h_bytes_per_step": H * (W // 2 + 1) * 8, "ms_per_step": dt * 1e3,
                "call": "numba_r2c via rocket_fft_b200.r2c(numpy pinned in/out), one image per step per rank"}
         # cheap parity spot check of the e2e result against the device-resident result
+        step()
+        torch.cuda.synchronize()
         chk = float(torch.linalg.vector_norm(torch.view_as_real(hX[:4].to(dev) - X[0, :4])) /
                     torch.linalg.vector_norm(torch.view_as_real(X[0, :4])))
         e2e["matches_device_path_rel_l2"] = chk

@@ -1,0 +1,111 @@
+"""Multi-GPU drivers (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The reference is single-process CPU code: nothing to mirror here.
+Two ways the transform path shards:
+
+* batched transforms (configs 1, 2, 4, 5): independent lines / images -> every rank runs
+  the single-GPU plan on its own slice, no collective (`shard_batch`);
+* one large N-D transform (config 3, fftn of a 1024^3 volume): slab decomposition with ONE
+  exchange step.  Rank g owns planes [g*N0/P, (g+1)*N0/P) of axis 0:
+      1. local transforms over axes (1, 2) of the slab           (our kernels)
+      2. all-to-all: block (g -> h) = my planes x axis-1 range of h  (NCCL over NVLink)
+      3. local transform along axis 0 on (N0, N1/P, N2)          (our kernels)
+  The result is left in the TRANSPOSED distribution (axis 1 sharded, axis 0 complete),
+  which is what a following inverse transform wants; `transpose_back=True` adds the second
+  all-to-all that restores the input distribution.
+"""
+from __future__ import annotations
+
+import math
+
+
+def shard_batch(n_items: int, rank: int, world: int):
+    """Half-open range of batch items owned by `rank` (even split, remainder to the first ranks)."""
+    base, rem = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class SlabFFTN:
+    """fftn/ifftn of a 3-D complex volume sharded by slabs of axis 0 over a process group.
+
+    `local_c2c(ain, aout, axes, forward, fct)` is the single-device transform
+    (default: rocket_fft_b200.c2c on CUDA tensors).  All buffers are allocated once.
+    """
+
+    def __init__(self, shape, dtype, device, group=None, local_c2c=None, dist=None):
+        import torch
+
+        if dist is None:
+            import torch.distributed as dist
+        self.torch = torch
+        self.dist = dist
+        self.group = group
+        self.P = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        n0, n1, n2 = (int(s) for s in shape)
+        if n0 % self.P or n1 % self.P:
+            raise ValueError("axis 0 and axis 1 extents must be divisible by the number of ranks")
+        self.shape = (n0, n1, n2)
+        self.dtype = dtype
+        self.device = device
+        if local_c2c is None:
+            from . import lowlevel
+
+            local_c2c = lambda a, b, axes, fwd, fct: lowlevel.c2c(a, b, axes, fwd, fct)  # noqa: E731
+        self.c2c = local_c2c
+        P = self.P
+        self.local_in_shape = (n0 // P, n1, n2)
+        self.local_out_shape = (n0, n1 // P, n2)
+        self.send = torch.empty((P, n0 // P, n1 // P, n2), dtype=dtype, device=device)
+        self.recv = torch.empty((P, n0 // P, n1 // P, n2), dtype=dtype, device=device)
+        self.bytes_sent_per_rank = self.send.numel() * self.send.element_size() * (P - 1) // P
+        self.timings = {}
+
+    # -- pieces (exposed so the bench can time the exchange on its own) ---------------------
+    def local_planes(self, x, forward=True, fct=1.0):
+        """In-place transforms over axes (1, 2) of the local slab (n0/P, n1, n2)."""
+        self.c2c(x, x, [1, 2], forward, fct)
+        return x
+
+    def pack(self, x):
+        """(n0/P, n1, n2) -> send[h, i0, j, i2] = x[i0, h*n1/P + j, i2]."""
+        P = self.P
+        n0p, n1, n2 = self.local_in_shape
+        self.send.copy_(x.view(n0p, P, n1 // P, n2).permute(1, 0, 2, 3))
+        return self.send
+
+    def exchange(self):
+        self.dist.all_to_all_single(self.recv.view(-1), self.send.view(-1), group=self.group)
+        return self.recv
+
+    def local_axis0(self, forward=True):
+        """recv viewed as (n0, n1/P, n2): transform along axis 0 in place."""
+        y = self.recv.view(self.local_out_shape)
+        self.c2c(y, y, [0], forward, 1.0)
+        return y
+
+    def forward(self, x, forward=True, fct=1.0, transpose_back=False):
+        """x: this rank's slab (n0/P, n1, n2), overwritten.  Returns the local part of the
+        result: (n0, n1/P, n2) [axis-1 sharded] or, with transpose_back, (n0/P, n1, n2)."""
+        self.local_planes(x, forward, fct)
+        self.pack(x)
+        self.exchange()
+        y = self.local_axis0(forward)
+        if not transpose_back:
+            return y
+        P = self.P
+        n0, n1p, n2 = self.local_out_shape
+        # second exchange: block (h -> g) = axis-0 range of g x my axis-1 range
+        self.send.copy_(y.view(P, n0 // P, n1p, n2))
+        self.dist.all_to_all_single(self.recv.view(-1), self.send.view(-1), group=self.group)
+        # recv[h, i0, j, i2] holds x[i0, h*n1/P + j, i2]
+        x.view(n0 // P, P, n1p, n2).copy_(self.recv.permute(1, 0, 2, 3))
+        return x
+
+    @staticmethod
+    def flops(shape):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        return 5.0 * n * math.log2(n)

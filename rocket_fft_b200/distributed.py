@@ -33,7 +33,7 @@ class SlabFFTN:
     (default: rocket_fft_b200.c2c on CUDA tensors).  All buffers are allocated once.
     """
 
-    def __init__(self, shape, dtype, device, group=None, local_c2c=None, dist=None):
+    def __init__(self, shape, dtype, device, group=None, local_c2c=None, dist=None, exchange="auto"):
         import torch
 
         if dist is None:
@@ -57,9 +57,32 @@ class SlabFFTN:
         P = self.P
         self.local_in_shape = (n0 // P, n1, n2)
         self.local_out_shape = (n0, n1 // P, n2)
-        self.send = torch.empty((P, n0 // P, n1 // P, n2), dtype=dtype, device=device)
-        self.recv = torch.empty((P, n0 // P, n1 // P, n2), dtype=dtype, device=device)
-        self.bytes_sent_per_rank = self.send.numel() * self.send.element_size() * (P - 1) // P
+        blk = (P, n0 // P, n1 // P, n2)
+        self.bytes_sent_per_rank = n0 // P * n1 * n2 * torch.empty((), dtype=dtype).element_size() * (P - 1) // P
+        # Exchange engine.  "symm": peer-mapped symmetric receive buffers (torch symmetric memory
+        # over NVLink P2P): every rank PUSHES its strided blocks straight into the peers' receive
+        # buffers -- the pack pass disappears and no NCCL staging is involved.  "nccl": pack +
+        # all_to_all_single.  "auto": symm on CUDA when it can be set up, else nccl.
+        self.mode = "nccl"
+        self.hdl = None
+        if exchange in ("auto", "symm") and str(device).startswith("cuda"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                self.recv = symm_mem.empty(blk, dtype=dtype, device=device)
+                gname = (group if group is not None else dist.group.WORLD).group_name
+                self.hdl = symm_mem.rendezvous(self.recv, gname)
+                self.peer_recv = [self.hdl.get_buffer(h, blk, dtype) for h in range(P)]
+                self.streams = [torch.cuda.Stream(device=device) for _ in range(min(P, 4))]
+                self.mode = "symm"
+            except Exception as e:  # pragma: no cover - depends on the box
+                if exchange == "symm":
+                    raise
+                self.symm_error = repr(e)
+                self.hdl = None
+        if self.mode == "nccl":
+            self.recv = torch.empty(blk, dtype=dtype, device=device)
+            self.send = torch.empty(blk, dtype=dtype, device=device)
         self.timings = {}
 
     # -- pieces (exposed so the bench can time the exchange on its own) ---------------------
@@ -69,14 +92,36 @@ class SlabFFTN:
         return x
 
     def pack(self, x):
-        """(n0/P, n1, n2) -> send[h, i0, j, i2] = x[i0, h*n1/P + j, i2]."""
+        """(n0/P, n1, n2) -> send[h, i0, j, i2] = x[i0, h*n1/P + j, i2]  (nccl mode only)."""
         P = self.P
         n0p, n1, n2 = self.local_in_shape
         self.send.copy_(x.view(n0p, P, n1 // P, n2).permute(1, 0, 2, 3))
         return self.send
 
-    def exchange(self):
-        self.dist.all_to_all_single(self.recv.view(-1), self.send.view(-1), group=self.group)
+    def exchange(self, x=None):
+        """Move block (g -> h) for all h.  symm mode reads the strided slab `x` directly."""
+        if self.mode == "nccl":
+            if x is not None:
+                self.pack(x)
+            self.dist.all_to_all_single(self.recv.view(-1), self.send.view(-1), group=self.group)
+            return self.recv
+        torch = self.torch
+        P, g = self.P, self.rank
+        n0p, n1, n2 = self.local_in_shape
+        xv = x.view(n0p, P, n1 // P, n2)
+        cur = torch.cuda.current_stream()
+        self.hdl.barrier(channel=0)  # peers are done reading their receive buffers
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for off in range(P):
+            h = (g + off) % P  # staggered so that no peer is hit by everyone at once
+            st = self.streams[off % len(self.streams)]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                self.peer_recv[h][g].copy_(xv[:, h])
+        for st in self.streams:
+            cur.wait_stream(st)
+        self.hdl.barrier(channel=1)  # everybody's pushes have landed
         return self.recv
 
     def local_axis0(self, forward=True):
@@ -89,18 +134,18 @@ class SlabFFTN:
         """x: this rank's slab (n0/P, n1, n2), overwritten.  Returns the local part of the
         result: (n0, n1/P, n2) [axis-1 sharded] or, with transpose_back, (n0/P, n1, n2)."""
         self.local_planes(x, forward, fct)
-        self.pack(x)
-        self.exchange()
+        self.exchange(x)
         y = self.local_axis0(forward)
         if not transpose_back:
             return y
         P = self.P
         n0, n1p, n2 = self.local_out_shape
-        # second exchange: block (h -> g) = axis-0 range of g x my axis-1 range
-        self.send.copy_(y.view(P, n0 // P, n1p, n2))
-        self.dist.all_to_all_single(self.recv.view(-1), self.send.view(-1), group=self.group)
-        # recv[h, i0, j, i2] holds x[i0, h*n1/P + j, i2]
-        x.view(n0 // P, P, n1p, n2).copy_(self.recv.permute(1, 0, 2, 3))
+        # second exchange (NCCL): block (h -> g) = axis-0 range of g x my axis-1 range
+        send = y.view(P, n0 // P, n1p, n2).clone()
+        back = self.torch.empty_like(send)
+        self.dist.all_to_all_single(back.view(-1), send.view(-1), group=self.group)
+        # back[h, i0, j, i2] holds X[i0, h*n1/P + j, i2]
+        x.view(n0 // P, P, n1p, n2).copy_(back.permute(1, 0, 2, 3))
         return x
 
     @staticmethod

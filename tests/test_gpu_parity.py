@@ -361,3 +361,40 @@ def test_device_arrays_and_full_size_properties(R):
     R.dct(y, y, [0, 1], 3, 1.0 / (4096.0 * 4096.0), False)
     err = float(torch.linalg.vector_norm(y - x) / torch.linalg.vector_norm(x))
     assert err < parity.tol(np.float64, 4096 * 4096), err
+
+
+def test_numba_njit_calls_run_on_the_gpu(R):
+    """The reference's own usage pattern (tests/test_low_level_interface.py:30-51): low-level
+    functions called from nogil @njit code on NumPy arrays, here bound to librocketfft_b200."""
+    import numba as nb
+
+    from rocket_fft_b200 import numba_api as napi
+
+    @nb.njit(nogil=True)
+    def jit_c2c(ain, aout, axes, forward, fct, nthreads):
+        napi.c2c(ain, aout, axes, forward, fct, nthreads)
+        return aout
+
+    @nb.njit(nogil=True)
+    def jit_hartley(ain, aout, axes, fct, nthreads):
+        napi.r2r_genuine_hartley(ain, aout, axes, fct, nthreads)
+        return aout
+
+    rng = np.random.default_rng(8)
+    x = cplx(rng, (32, 17, 39), np.complex128)
+    want = np.fft.fftn(x)
+    for axes_dtype in (np.int64, np.uint64, np.int32, np.uint8, np.float64):
+        out = np.empty_like(x)
+        axes = np.arange(3).astype(axes_dtype)
+        R.launch_count_reset()
+        jit_c2c(x, out, axes, True, 1.0, 1)
+        assert R.launch_count() > 0
+        check(out, want, np.float64, x.size, axes_dtype)
+    v1 = x.real.copy()
+    assert jit_c2c(x, x, np.arange(3), True, np.float32(1.0), np.int16(4)) is x
+    check(x, want, np.float64, x.size, "in place")
+    a = rng.random((128, 129)) - 0.5
+    out = np.empty_like(a)
+    jit_hartley(a, out, np.arange(2), 1.0, 1)
+    w = np.fft.fftn(a)
+    check(out, w.real + w.imag, np.float64, a.size, "hartley")

@@ -1,0 +1,319 @@
+"""numpy.fft / scipy.fft style functions on top of the low-level API -- the layer directly above
+the transform path (reference: rocket_fft/overloads.py).
+
+Argument handling follows the reference's host helpers, re-implemented here:
+  * shape/axes normalisation (`s`/`n`, `axes`, negative axes; O:421-489), zero-pad-or-crop
+    (O:575-609), dtype promotion to float32/float64/complex64/complex128 (O:48-64);
+  * `norm` -> `fct` (O:513-551), with the 2(N+delta) factors of DCT/DST (O:505-510, 1012-1013);
+  * DCT/DST type inversion 2<->3 for the inverse transforms (O:704-712), `orthogonalize` (O:715-732);
+  * real input to fft/fftn goes through c2c_sym (O:958-968), irfft*/hfft through c2r with the
+    output length rule n = 2(m-1) unless given (O:644-657).
+Inputs may be NumPy arrays (host path) or torch CUDA tensors (device path, no copies beyond
+pad/crop); the result lives where the input lives.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import lowlevel as _ll
+
+
+# ---------------------------------------------------------------------------------------------
+# tiny array-backend shim (numpy or torch)
+# ---------------------------------------------------------------------------------------------
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _np_dtype(x):
+    if _is_torch(x):
+        return np.dtype(str(x.dtype).replace("torch.", ""))
+    return np.asarray(x).dtype
+
+
+def _torch_dtype(dt):
+    import torch
+
+    return getattr(torch, np.dtype(dt).name)
+
+
+def _as_dtype(x, dt):
+    if _is_torch(x):
+        return x if _np_dtype(x) == dt else x.to(_torch_dtype(dt))
+    x = np.asarray(x)
+    return x if x.dtype == dt else x.astype(dt)
+
+
+def _empty(like, shape, dt):
+    if _is_torch(like):
+        import torch
+
+        return torch.empty(tuple(shape), dtype=_torch_dtype(dt), device=like.device)
+    return np.empty(tuple(shape), dtype=dt)
+
+
+def _zeros(like, shape, dt):
+    out = _empty(like, shape, dt)
+    if _is_torch(out):
+        out.zero_()
+    else:
+        out[...] = 0
+    return out
+
+
+def _real_of(dt):
+    dt = np.dtype(dt)
+    if dt in (np.dtype(np.complex64), np.dtype(np.float32), np.dtype(np.float16)):
+        return np.dtype(np.float32)
+    return np.dtype(np.float64)
+
+
+def _cplx_of(dt):
+    return np.dtype(np.complex64) if _real_of(dt) == np.dtype(np.float32) else np.dtype(np.complex128)
+
+
+def _is_complex(dt):
+    return np.dtype(dt).kind == "c"
+
+
+# ---------------------------------------------------------------------------------------------
+# argument normalisation
+# ---------------------------------------------------------------------------------------------
+def _shape_axes(x, s, axes, default_all):
+    nd = len(x.shape)
+    if axes is None:
+        if s is None:
+            axes = list(range(nd)) if default_all else [nd - 1]
+        else:
+            axes = list(range(nd - len(s), nd))
+    else:
+        axes = [int(a) for a in (axes if hasattr(axes, "__len__") else [axes])]
+    axes = [a + nd if a < 0 else a for a in axes]
+    for a in axes:
+        if not 0 <= a < nd:
+            raise ValueError("axes exceeds dimensionality of input")
+    if s is None:
+        s = [x.shape[a] for a in axes]
+    else:
+        s = [int(v) for v in (s if hasattr(s, "__len__") else [s])]
+        if len(s) != len(axes):
+            raise ValueError("When given, axes and shape arguments have to be of the same length.")
+        s = [x.shape[a] if v == -1 else v for v, a in zip(s, axes)]
+    for v in s:
+        if v < 1:
+            raise ValueError(f"invalid number of data points ({v}) specified")
+    return s, axes
+
+
+def _pad_or_crop(x, s, axes, dt):
+    x = _as_dtype(x, dt)
+    shape = list(x.shape)
+    changed = False
+    for v, a in zip(s, axes):
+        if shape[a] != v:
+            shape[a] = v
+            changed = True
+    if not changed:
+        return x
+    out = _zeros(x, shape, dt)
+    sl = tuple(slice(0, min(a, b)) for a, b in zip(shape, x.shape))
+    out[sl] = x[sl]
+    return out
+
+
+def _fct(shape, axes, norm, forward, delta=None):
+    n = 1.0
+    for a in axes:
+        n *= shape[a] if delta is None else 2.0 * (shape[a] + delta)
+    if norm is None or norm == "backward":
+        return 1.0 if forward else 1.0 / n
+    if norm == "ortho":
+        return 1.0 / math.sqrt(n)
+    if norm == "forward":
+        return 1.0 / n if forward else 1.0
+    raise ValueError("Invalid norm value; should be 'backward', 'ortho' or 'forward'.")
+
+
+# ---------------------------------------------------------------------------------------------
+# complex / real transforms
+# ---------------------------------------------------------------------------------------------
+def _c2cn(x, s, axes, norm, forward, default_all):
+    s, axes = _shape_axes(x, s, axes, default_all)
+    dt = _np_dtype(x)
+    cdt = _cplx_of(dt)
+    if _is_complex(dt):
+        x = _pad_or_crop(x, s, axes, cdt)
+        out = _empty(x, x.shape, cdt)
+        _ll.c2c(x, out, axes, forward, _fct(x.shape, axes, norm, forward))
+    else:
+        x = _pad_or_crop(x, s, axes, _real_of(dt))
+        out = _empty(x, x.shape, cdt)
+        _ll.c2c_sym(x, out, axes, forward, _fct(x.shape, axes, norm, forward))
+    return out
+
+
+def _r2cn(x, s, axes, norm, forward, default_all):
+    dt = _np_dtype(x)
+    if _is_complex(dt):
+        raise TypeError(f"unsupported dtype {dt}")
+    s, axes = _shape_axes(x, s, axes, default_all)
+    rdt = _real_of(dt)
+    x = _pad_or_crop(x, s, axes, rdt)
+    shape = list(x.shape)
+    shape[axes[-1]] = shape[axes[-1]] // 2 + 1
+    out = _empty(x, shape, _cplx_of(rdt))
+    _ll.r2c(x, out, axes, forward, _fct(x.shape, axes, norm, forward))
+    return out
+
+
+def _c2rn(x, s, axes, norm, forward, default_all):
+    s_given = s is not None
+    s, axes = _shape_axes(x, s, axes, default_all)
+    cdt = _cplx_of(_np_dtype(x))
+    last = axes[-1]
+    n_last = s[-1] if s_given else 2 * (x.shape[last] - 1)
+    if n_last < 1:
+        raise ValueError(f"Invalid number of data points ({n_last}) specified")
+    s_in = list(s)
+    s_in[-1] = n_last // 2 + 1
+    xin = _pad_or_crop(x, s_in, axes, cdt)
+    shape = list(xin.shape)
+    shape[last] = n_last
+    out = _empty(xin, shape, _real_of(cdt))
+    _ll.c2r(xin, out, axes, forward, _fct(shape, axes, norm, forward))
+    return out
+
+
+def fft(x, n=None, axis=-1, norm=None):
+    return _c2cn(x, None if n is None else [n], [axis], norm, True, False)
+
+
+def ifft(x, n=None, axis=-1, norm=None):
+    return _c2cn(x, None if n is None else [n], [axis], norm, False, False)
+
+
+def fft2(x, s=None, axes=(-2, -1), norm=None):
+    return _c2cn(x, s, axes, norm, True, True)
+
+
+def ifft2(x, s=None, axes=(-2, -1), norm=None):
+    return _c2cn(x, s, axes, norm, False, True)
+
+
+def fftn(x, s=None, axes=None, norm=None):
+    return _c2cn(x, s, axes, norm, True, True)
+
+
+def ifftn(x, s=None, axes=None, norm=None):
+    return _c2cn(x, s, axes, norm, False, True)
+
+
+def rfft(x, n=None, axis=-1, norm=None):
+    return _r2cn(x, None if n is None else [n], [axis], norm, True, False)
+
+
+def irfft(x, n=None, axis=-1, norm=None):
+    return _c2rn(x, None if n is None else [n], [axis], norm, False, False)
+
+
+def rfft2(x, s=None, axes=(-2, -1), norm=None):
+    return _r2cn(x, s, axes, norm, True, True)
+
+
+def irfft2(x, s=None, axes=(-2, -1), norm=None):
+    return _c2rn(x, s, axes, norm, False, True)
+
+
+def rfftn(x, s=None, axes=None, norm=None):
+    return _r2cn(x, s, axes, norm, True, True)
+
+
+def irfftn(x, s=None, axes=None, norm=None):
+    return _c2rn(x, s, axes, norm, False, True)
+
+
+def hfft(x, n=None, axis=-1, norm=None):
+    """FFT of a Hermitian-symmetric signal (real spectrum): c2r with the forward sign."""
+    return _c2rn(x, None if n is None else [n], [axis], norm, True, False)
+
+
+def ihfft(x, n=None, axis=-1, norm=None):
+    return _r2cn(x, None if n is None else [n], [axis], norm, False, False)
+
+
+# ---------------------------------------------------------------------------------------------
+# DCT / DST
+# ---------------------------------------------------------------------------------------------
+def _r2rn(x, type, s, axes, norm, orthogonalize, forward, cosine, default_all):
+    type = int(type)
+    if type not in (1, 2, 3, 4):
+        raise ValueError("Invalid type; must be one of (1, 2, 3, 4).")
+    s, axes = _shape_axes(x, s, axes, default_all)
+    dt = _np_dtype(x)
+    if not forward:
+        type = {1: 1, 2: 3, 3: 2, 4: 4}[type]
+    delta = (-1.0 if cosine else 1.0) if type == 1 else 0.0
+    ortho = (norm == "ortho") if orthogonalize is None else bool(orthogonalize)
+    fn = _ll.dct if cosine else _ll.dst
+    if _is_complex(dt):
+        cdt = _cplx_of(dt)
+        x = _pad_or_crop(x, s, axes, cdt)
+        out = _empty(x, x.shape, cdt)
+        fct = _fct(out.shape, axes, norm, forward, delta)
+        for part in ("real", "imag"):
+            xi, oi = getattr(x, part), getattr(out, part)
+            if not _is_torch(x):
+                fn(xi, oi, axes, type, fct, ortho)
+            else:
+                import torch
+
+                xr = torch.view_as_real(x)[..., 0 if part == "real" else 1]
+                orr = torch.view_as_real(out)[..., 0 if part == "real" else 1]
+                fn(xr, orr, axes, type, fct, ortho)
+        return out
+    rdt = _real_of(dt)
+    x = _pad_or_crop(x, s, axes, rdt)
+    out = _empty(x, x.shape, rdt)
+    fn(x, out, axes, type, _fct(out.shape, axes, norm, forward, delta), ortho)
+    return out
+
+
+def dct(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+    return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, True, True, False)
+
+
+def idct(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+    return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, False, True, False)
+
+
+def dst(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+    return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, True, False, False)
+
+
+def idst(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+    return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, False, False, False)
+
+
+def dctn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+    return _r2rn(x, type, s, axes, norm, orthogonalize, True, True, True)
+
+
+def idctn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+    return _r2rn(x, type, s, axes, norm, orthogonalize, False, True, True)
+
+
+def dstn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+    return _r2rn(x, type, s, axes, norm, orthogonalize, True, False, True)
+
+
+def idstn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+    return _r2rn(x, type, s, axes, norm, orthogonalize, False, False, True)
+
+
+def next_fast_len(target, real=False):
+    """scipy.fft.next_fast_len (O:1862-1870 -> numba_good_size)."""
+    if target < 0:
+        raise ValueError("Target cannot be negative.")
+    return _ll.good_size(int(target), bool(real))

@@ -126,7 +126,39 @@ struct Pow2Body {
             // (memory-level parallelism: 16 independent requests per thread in flight).
             const bool packed_vec = (MODE == 1) && g.in_sa == (int64_t)sizeof(T);
             const bool plain = (MODE == 0) && g.load_mode == LD_C2C && g.n_in == (uint32_t)N;
-            if (packed_vec || plain) {
+            if (MODE == 2) {
+                // Packed inverse real transform: the N+1 Hermitian bins X are folded into the N-point
+                // complex spectrum  Z[e] = (X[e] + conj X[N-e]) + i w^e (X[e] - conj X[N-e]),
+                // w = exp(+2 pi i/(2N)), whose backward DFT is x[2m] + i x[2m+1].  Im X[0], Im X[N]
+                // are ignored (reference: general_c2r, H:3830, 3845-3846).  forward=true: X -> conj X.
+                const bool cj = g.backward == 0;
+                const int64_t sa = g.in_sa;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    C a[8], b[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = h * 8 + i;
+                        const int e = t + (idx / R) * TPL + (idx % R) * ido;
+                        a[i] = wok ? *reinterpret_cast<const C *>(line + (int64_t)e * sa) : mk<T>(T(0), T(0));
+                        b[i] = wok ? *reinterpret_cast<const C *>(line + (int64_t)(N - e) * sa) : mk<T>(T(0), T(0));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = h * 8 + i;
+                        const int e = t + (idx / R) * TPL + (idx % R) * ido;
+                        C A = a[i], B = b[i];
+                        if (e == 0) { A.y = T(0); B.y = T(0); }
+                        if (cj) { A.y = -A.y; B.y = -B.y; }
+                        const C s = mk<T>(A.x + B.x, A.y - B.y);
+                        const C d = mk<T>(A.x - B.x, A.y + B.y);
+                        const C wc = __ldg(g.twA + e);           // exp(-2 pi i e/(2N))
+                        const C wd = cmulc(d, wc);                // d * conj(wc)
+                        const C z = mk<T>(s.x - wd.y, s.y + wd.x);  // s + i*wd
+                        v[idx] = cswap(z);
+                    }
+                }
+            } else if (packed_vec || plain) {
                 const int64_t sa = packed_vec ? (int64_t)(2 * sizeof(T)) : g.in_sa;
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
@@ -182,6 +214,26 @@ struct Pow2Body {
         constexpr int RL = PL::radix(PL::NPASS - 1), NBL = 16 / RL;
         int w, t;
         map(PL::NPASS > 1 ? lf_out : lf_in, tid, w, t);
+        if (MODE == 2) {
+            // bins hold swap(x[2k] + i x[2k+1]); deliver the two reals
+            if (w >= wvalid) return;
+            char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
+            const T f = g.fct;
+            const bool vec = g.out_sa == (int64_t)sizeof(T) && g.flags == 0;  // flags bit0: output not complex-aligned
+#pragma unroll
+            for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const int k = t + j * TPL + q * (N / RL);
+                    const C val = mk<T>(v[j * RL + q].y * f, v[j * RL + q].x * f);
+                    if (vec) *reinterpret_cast<C *>(line + (int64_t)k * 2 * sizeof(T)) = val;
+                    else {
+                        *reinterpret_cast<T *>(line + (int64_t)(2 * k) * g.out_sa) = val.x;
+                        *reinterpret_cast<T *>(line + (int64_t)(2 * k + 1) * g.out_sa) = val.y;
+                    }
+                }
+            return;
+        }
         if (MODE == 0) {
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];

@@ -17,11 +17,18 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
     using Body = Pow2Body<T, LOGN, W, MODE>;
     TileGeom<T> g;
     LineJob j2 = job;
-    if (MODE == 1) j2.n = job.n / 2;  // geometry in complex points
+    if (MODE != 0) j2.n = job.n / 2;  // geometry in complex points
     const uint64_t ntiles = fill_geom<T>(g, j2, dims, (uint32_t)W, load_lf, store_lf);
-    if (MODE == 1) {
+    if (MODE != 0) {
         g.n_out = (uint32_t)(job.n / 2 + 1);
         g.twA = (const cx<T> *)get_table(TAB_LINE, job.prec, job.n, 0);
+    }
+    if (MODE == 2) {
+        // the two reals of an output point are stored as one complex value when aligned
+        const uint64_t csz = 2 * sizeof(T);
+        bool al = ((uint64_t)(uintptr_t)job.out % csz) == 0;
+        for (auto &d : dims) al = al && (d.os % (int64_t)csz) == 0;
+        g.flags = al ? 0 : 1;
     }
     const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
     const size_t smem = (size_t)W * Body::PITCH * sizeof(cx<T>);
@@ -44,9 +51,10 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     constexpr bool dbl = sizeof(T) == 8;
     constexpr int WE = p2_we(LOGN), WL = p2_wl(LOGN, dbl);
     const bool lf = load_lf || store_lf;
-    if (mode == 1) {
+    if (mode != 0) {
         if (lf) return false;
-        launch_pow2_inst<T, LOGN, WE, 1>(job, dims, load_lf, store_lf, s);
+        if (mode == 1) launch_pow2_inst<T, LOGN, WE, 1>(job, dims, load_lf, store_lf, s);
+        else launch_pow2_inst<T, LOGN, WE, 2>(job, dims, load_lf, store_lf, s);
         return true;
     }
     if (!lf) {
@@ -75,6 +83,10 @@ bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load
         for (auto &d : dims) al = al && (d.is % (int64_t)csz) == 0;
         if (!al && job.is == (int64_t)sizeof(T)) return false;
         mode = 1;
+        n /= 2;
+    } else if (job.load_mode == LD_HERM && job.store_mode == ST_REAL && job.flags == 0 && job.twN == 0 && (n % 2 == 0) &&
+               !load_lf && !store_lf && n >= 32) {
+        mode = 2;
         n /= 2;
     } else if (job.store_mode == ST_HC) return false;
     if (n < 16 || (n & (n - 1))) return false;

@@ -359,12 +359,11 @@ static bool choose_split(uint64_t n, int prec, uint64_t &n1, uint64_t &n2) {
     return true;
 }
 
-void run_lines(const LineJob &job_in, cudaStream_t s) {
-    LineJob job = job_in;
-    if (job.n == 0) return;
-    std::vector<Dim> dims;
+// drop unit dims, sort by stride; false if the job is empty
+static bool normalise(LineJob &job, std::vector<Dim> &dims) {
+    if (job.n == 0) return false;
     for (auto &d : job.batch) {
-        if (d.n == 0) return;
+        if (d.n == 0) return false;
         if (d.n >= (1ll << 31)) { set_error("array dimension too large"); throw Error(); }
         if (d.n == 1) continue;
         dims.push_back(d);
@@ -377,8 +376,29 @@ void run_lines(const LineJob &job_in, cudaStream_t s) {
         return std::min(iabs64(a.is), iabs64(a.os)) < std::min(iabs64(b.is), iabs64(b.os));
     });
     if (total_lines(dims) >= (1ull << 31)) { set_error("too many lines"); throw Error(); }
+    return true;
+}
 
+void run_lines(const LineJob &job_in, cudaStream_t s) {
+    LineJob job = job_in;
+    std::vector<Dim> dims;
+    if (!normalise(job, dims)) return;
     run_norm(job, dims, s);
+}
+
+static bool pow2_try(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    if (dims.size() > (size_t)MAXB) return false;
+    if (!alignment_ok(job, dims)) return false;
+    const bool load_lf = !dims.empty() && iabs64(dims[0].is) < iabs64(job.is);
+    const bool store_lf = !dims.empty() && iabs64(dims[0].os) < iabs64(job.os);
+    return job.prec ? launch_pow2_f64(job, dims, load_lf, store_lf, s) : launch_pow2_f32(job, dims, load_lf, store_lf, s);
+}
+
+bool run_lines_pow2(const LineJob &job_in, cudaStream_t s) {
+    LineJob job = job_in;
+    std::vector<Dim> dims;
+    if (!normalise(job, dims)) return true;
+    return pow2_try(job, dims, s);
 }
 
 // dims: extent > 1, sorted by stride (dims[0] = the tile dim)

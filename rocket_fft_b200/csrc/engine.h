@@ -34,6 +34,8 @@ struct LineJob {
 };
 
 void run_lines(const LineJob &job, cudaStream_t stream);
+// Only the register-resident power-of-two kernel; false (nothing launched) if it does not take the job.
+bool run_lines_pow2(const LineJob &job, cudaStream_t stream);
 
 // N-D array description as it arrives through the ABI.
 struct NdArgs {

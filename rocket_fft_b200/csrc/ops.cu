@@ -463,6 +463,22 @@ void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s)
         } else p.Lf = (uint32_t)(2 * N);
         const auto &si = first ? a.sin : a.sout;
         std::vector<Dim> b = batch_dims(a.shape, si, a.sout, ax);
+        if ((type == 2 || type == 3) && N % 2 == 0) {
+            // power-of-two half length: one fused kernel (reorder + packed real FFT + phase factors)
+            LineJob fj;
+            fj.prec = a.prec;
+            fj.n = N;
+            fj.in = first ? a.in : a.out;
+            fj.out = a.out;
+            fj.is = si[ax];
+            fj.os = a.sout[ax];
+            fj.batch = b;
+            fj.fct = first ? a.fct : 1.0;
+            fj.load_mode = type == 2 ? LD_DCT2 : LD_DCT3;
+            fj.store_mode = type == 2 ? ST_DCT2 : ST_DCT3;
+            fj.flags = (cosine ? 0 : FLAG_SINE) | (ortho ? FLAG_ORTHO : 0) | (g_dst_quirk ? FLAG_QUIRK : 0);
+            if (run_lines_pow2(fj, s)) { first = false; continue; }
+        }
         LinesIdx bi;
         memset(&bi, 0, sizeof(bi));
         uint64_t nlines = 1;

@@ -158,6 +158,69 @@ struct Pow2Body {
                         v[idx] = cswap(z);
                     }
                 }
+            } else if (MODE == 3) {
+                // DCT-II / DST-II of a real line of length 2N (N = complex points here): Makhoul's
+                // reordering v = [x0, x2, x4, ..., x5, x3, x1] packed two-by-two into complex points;
+                // the sine transform alternates the sign of the odd samples.
+                const bool sine = (g.flags & FLAG_SINE) != 0;
+                const int64_t sa = g.in_sa;
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const int e = t + j * TPL + m * ido;
+                        const bool lo = e < N / 2;
+                        const int i0 = lo ? 4 * e : 4 * N - 1 - 4 * e;
+                        const int i1 = lo ? 4 * e + 2 : 4 * N - 3 - 4 * e;
+                        C val = mk<T>(T(0), T(0));
+                        if (wok) {
+                            val.x = *reinterpret_cast<const T *>(line + (int64_t)i0 * sa);
+                            val.y = *reinterpret_cast<const T *>(line + (int64_t)i1 * sa);
+                        }
+                        if (sine && !lo) { val.x = -val.x; val.y = -val.y; }
+                        v[j * R + m] = val;
+                    }
+            } else if (MODE == 4) {
+                // DCT-III / DST-III: the Hermitian spectrum H_k = conj(c_k) (x_k - i x_{2N-k}),
+                // c_k = exp(-i pi k / (4N)), of the reordered output is built on the fly and folded into
+                // the packed inverse real transform exactly as in MODE 2.
+                const bool sine = (g.flags & FLAG_SINE) != 0, ortho = (g.flags & FLAG_ORTHO) != 0;
+                const int NR = 2 * N;  // real length
+                const int scaled = (sine && (g.flags & FLAG_QUIRK) == 0) ? NR - 1 : 0;  // caller's index scaled by sqrt2
+                const int64_t sa = g.in_sa;
+                auto ld = [&](int k) -> T {  // transform's element k (k == NR reads as 0)
+                    if (k >= NR || !wok) return T(0);
+                    const int io = sine ? NR - 1 - k : k;
+                    T r = *reinterpret_cast<const T *>(line + (int64_t)io * sa);
+                    if (ortho && io == scaled) r *= T(1.4142135623730951);
+                    return r;
+                };
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    T r[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = h * 4 + i;
+                        const int e = t + (idx / R) * TPL + (idx % R) * ido;
+                        r[i][0] = ld(e);
+                        r[i][1] = ld(NR - e);
+                        r[i][2] = ld(N - e);
+                        r[i][3] = ld(N + e);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = h * 4 + i;
+                        const int e = t + (idx / R) * TPL + (idx % R) * ido;
+                        const C ce = __ldg(g.twB + e), cm = __ldg(g.twB + (N - e));
+                        C A = cmulc(mk<T>(r[i][0], -r[i][1]), ce);
+                        C B = cmulc(mk<T>(r[i][2], -r[i][3]), cm);
+                        if (e == 0) { A.y = T(0); B.y = T(0); }
+                        const C s = mk<T>(A.x + B.x, A.y - B.y);
+                        const C d = mk<T>(A.x - B.x, A.y + B.y);
+                        const C wd = cmulc(d, __ldg(g.twA + e));
+                        v[idx] = cswap(mk<T>(s.x - wd.y, s.y + wd.x));
+                    }
+                }
             } else if (packed_vec || plain) {
                 const int64_t sa = packed_vec ? (int64_t)(2 * sizeof(T)) : g.in_sa;
 #pragma unroll
@@ -214,19 +277,28 @@ struct Pow2Body {
         constexpr int RL = PL::radix(PL::NPASS - 1), NBL = 16 / RL;
         int w, t;
         map(PL::NPASS > 1 ? lf_out : lf_in, tid, w, t);
-        if (MODE == 2) {
+        if (MODE == 2 || MODE == 4) {
             // bins hold swap(x[2k] + i x[2k+1]); deliver the two reals
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
             const T f = g.fct;
-            const bool vec = g.out_sa == (int64_t)sizeof(T) && g.flags == 0;  // flags bit0: output not complex-aligned
+            const bool vec = MODE == 2 && g.out_sa == (int64_t)sizeof(T) && g.flags == 0;  // flags bit0: output not complex-aligned
+            const bool sine = MODE == 4 && (g.flags & FLAG_SINE) != 0;
 #pragma unroll
             for (int j = 0; j < NBL; ++j)
 #pragma unroll
                 for (int q = 0; q < RL; ++q) {
                     const int k = t + j * TPL + q * (N / RL);
-                    const C val = mk<T>(v[j * RL + q].y * f, v[j * RL + q].x * f);
-                    if (vec) *reinterpret_cast<C *>(line + (int64_t)k * 2 * sizeof(T)) = val;
+                    C val = mk<T>(v[j * RL + q].y * f, v[j * RL + q].x * f);
+                    if (MODE == 4) {
+                        // undo Makhoul's reordering; the sine transform carries (-1)^j
+                        const bool lo = k < N / 2;
+                        const int j0 = lo ? 4 * k : 4 * N - 1 - 4 * k;
+                        const int j1 = lo ? 4 * k + 2 : 4 * N - 3 - 4 * k;
+                        if (sine && !lo) { val.x = -val.x; val.y = -val.y; }
+                        *reinterpret_cast<T *>(line + (int64_t)j0 * g.out_sa) = val.x;
+                        *reinterpret_cast<T *>(line + (int64_t)j1 * g.out_sa) = val.y;
+                    } else if (vec) *reinterpret_cast<C *>(line + (int64_t)k * 2 * sizeof(T)) = val;
                     else {
                         *reinterpret_cast<T *>(line + (int64_t)(2 * k) * g.out_sa) = val.x;
                         *reinterpret_cast<T *>(line + (int64_t)(2 * k + 1) * g.out_sa) = val.y;
@@ -287,14 +359,33 @@ struct Pow2Body {
                 const C a = sl[k];
                 const C bz = sl[(N - k) & (N - 1)];
                 const C b = mk<T>(bz.x, -bz.y);
-                const C e = mk<T>((a.x + b.x) * half, (a.y + b.y) * half);
-                const C d = mk<T>((a.x - b.x) * half, (a.y - b.y) * half);
+                const T hh = (MODE == 3) ? g.fct : half;  // DCT: the factor 2 of y = 2 Re(c V) cancels the 1/2
+                const C e = mk<T>((a.x + b.x) * hh, (a.y + b.y) * hh);
+                const C d = mk<T>((a.x - b.x) * hh, (a.y - b.y) * hh);
                 const C wk = __ldg(g.twA + k);
                 // o = -i * wk * d
                 const C wd = cmul(wk, d);
                 const C o = mk<T>(wd.y, -wd.x);
                 C x0 = mk<T>(e.x + o.x, e.y + o.y);
                 C x1 = mk<T>(e.x - o.x, -(e.y - o.y));
+                if (MODE == 3) {
+                    // y[k] = Re(c_k V_k), y[2N-k] = -Im(c_k V_k) for V_k = x0 and V_{N-k} = x1
+                    const bool sine = (g.flags & FLAG_SINE) != 0, ortho = (g.flags & FLAG_ORTHO) != 0;
+                    const int NR = 2 * N;
+                    const int scaled = (sine && (g.flags & FLAG_QUIRK) != 0) ? NR - 1 : 0;  // cosine-order index scaled by 1/sqrt2
+                    auto put = [&](int idx, T val) {
+                        if (ortho && idx == scaled) val *= T(0.70710678118654752);
+                        const int pos = sine ? NR - 1 - idx : idx;
+                        *reinterpret_cast<T *>(line + (int64_t)pos * g.out_sa) = val;
+                    };
+                    const C p0 = cmul(__ldg(g.twB + k), x0);
+                    put(k, p0.x);
+                    if (k > 0) put(NR - k, -p0.y);
+                    const C p1 = cmul(__ldg(g.twB + (N - k)), x1);
+                    put(N - k, p1.x);
+                    put(N + k, -p1.y);
+                    return;
+                }
                 if (conj_out) { x0.y = -x0.y; x1.y = -x1.y; }
                 st_cx<T, true>(line + (int64_t)k * g.out_sa, x0);
                 st_cx<T, true>(line + (int64_t)(N - k) * g.out_sa, x1);

@@ -23,6 +23,7 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
         g.n_out = (uint32_t)(job.n / 2 + 1);
         g.twA = (const cx<T> *)get_table(TAB_LINE, job.prec, job.n, 0);
     }
+    if (MODE == 3 || MODE == 4) g.twB = (const cx<T> *)get_table(TAB_QUARTER, job.prec, job.n, 0);
     if (MODE == 2) {
         // the two reals of an output point are stored as one complex value when aligned
         const uint64_t csz = 2 * sizeof(T);
@@ -51,11 +52,25 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     constexpr bool dbl = sizeof(T) == 8;
     constexpr int WE = p2_we(LOGN), WL = p2_wl(LOGN, dbl);
     const bool lf = load_lf || store_lf;
-    if (mode != 0) {
+    if (mode == 1 || mode == 2) {
         if (lf) return false;
         if (mode == 1) launch_pow2_inst<T, LOGN, WE, 1>(job, dims, load_lf, store_lf, s);
         else launch_pow2_inst<T, LOGN, WE, 2>(job, dims, load_lf, store_lf, s);
         return true;
+    }
+    if (mode == 3 || mode == 4) {
+        // in place along a strided axis both sides are line-fast or both element-fast
+        if (!lf) {
+            if (mode == 3) launch_pow2_inst<T, LOGN, WE, 3>(job, dims, false, false, s);
+            else launch_pow2_inst<T, LOGN, WE, 4>(job, dims, false, false, s);
+            return true;
+        }
+        if constexpr (WL == 0) return false;
+        else {
+            if (mode == 3) launch_pow2_inst<T, LOGN, WL, 3>(job, dims, true, true, s);
+            else launch_pow2_inst<T, LOGN, WL, 4>(job, dims, true, true, s);
+            return true;
+        }
     }
     if (!lf) {
         launch_pow2_inst<T, LOGN, WE, 0>(job, dims, load_lf, store_lf, s);
@@ -88,7 +103,11 @@ bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load
                !load_lf && !store_lf && n >= 32) {
         mode = 2;
         n /= 2;
-    } else if (job.store_mode == ST_HC) return false;
+    } else if ((job.load_mode == LD_DCT2 && job.store_mode == ST_DCT2) || (job.load_mode == LD_DCT3 && job.store_mode == ST_DCT3)) {
+        if (n % 2 || n < 32 || job.twN) return false;
+        mode = job.load_mode == LD_DCT2 ? 3 : 4;
+        n /= 2;
+    } else if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
     if (n < 16 || (n & (n - 1))) return false;
     int logn = 0;
     while ((1ull << logn) < n) ++logn;

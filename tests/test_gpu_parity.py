@@ -248,6 +248,17 @@ def test_dct_dst(R, dt):
                 getattr(R, kind)(x, a, axes, t, 0.25, False)
                 getattr(T, kind)(x, b, axes, t, 0.25, False)
                 check(a, b, dt, 4 * x.size, (kind, t, axes))
+    # strided power-of-two lines (fused kernel, line-fast tiles), both precisions, in place
+    x = rng.standard_normal((64, 128, 24)).astype(dt)
+    for kind in ("dct", "dst"):
+        for t in (2, 3):
+            for ortho in (False, True):
+                for axes in ([0], [1], [0, 1], [1, 0]):
+                    b = np.empty_like(x)
+                    getattr(T, kind)(x, b, axes, t, 0.5, ortho)
+                    a = x.copy()
+                    getattr(R, kind)(a, a, axes, t, 0.5, ortho)
+                    check(a, b, dt, 4 * 64 * 128, (kind, t, axes, ortho, "inplace strided"))
     # FFTW known answers (tests/test_scipy_testsuite.py:1192-1293)
     d, _ = parity.golden()
     for k in [k for k in d.files if k.startswith("fftw_")]:

@@ -15,6 +15,30 @@ template <typename T> __host__ __device__ __forceinline__ cx<T> mk(T a, T b) {
 }
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+#if defined(__CUDA_ARCH__) && defined(RFB_USE_F32X2)
+// Blackwell packed single precision: one FADD2 per complex add/sub (PTX add/sub.f32x2, sm_100+).
+// Measured on B200 (round 1): 208 FADD2 instead of 424 FADD per thread in the 8192-point kernel, but
+// c2c c64 n=4096 dropped from 77.9 % to 70.2 % of HBM peak and the r2c row kernel gained < 1 % --
+// the kernels are latency/occupancy limited, not FP32-issue limited -- so this stays opt-in.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+    return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+    return r;
+}
+#endif
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
     C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
 }

@@ -76,8 +76,21 @@ struct Pow2Body {
             for (int j = 0; j < NB; ++j) {
                 const int i = (t + j * TPL) % ido;
                 const C *tw = stw + PL::twoff(P) + i;
+                if constexpr (R == 16 && sizeof(T) == 8 && ido >= 64) {
+                    // fp64: the table of a long pass (15*ido entries) does not stay in L1 next to the data;
+                    // load w^1..w^4 and build the other powers (error a few ulp << the 1e-13 budget)
+                    C w[16];
 #pragma unroll
-                for (int q = 1; q < R; ++q) v[j * R + q] = cmul(v[j * R + q], __ldg(tw + (q - 1) * ido));
+                    for (int q = 1; q <= 4; ++q) w[q] = __ldg(tw + (q - 1) * ido);
+                    w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]); w[8] = cmul(w[4], w[4]);
+#pragma unroll
+                    for (int q = 1; q <= 8; ++q) v[j * R + q] = cmul(v[j * R + q], w[q]);
+#pragma unroll
+                    for (int q = 9; q < 16; ++q) v[j * R + q] = cmul(v[j * R + q], cmul(w[8], w[q - 8]));
+                } else {
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[j * R + q] = cmul(v[j * R + q], __ldg(tw + (q - 1) * ido));
+                }
             }
         }
     }
@@ -221,8 +234,15 @@ struct Pow2Body {
                         v[idx] = cswap(mk<T>(s.x - wd.y, s.y + wd.x));
                     }
                 }
-            } else if (packed_vec || plain) {
-                const int64_t sa = packed_vec ? (int64_t)(2 * sizeof(T)) : g.in_sa;
+            } else if (packed_vec || (plain && g.in_sa == (int64_t)sizeof(C))) {
+                // contiguous line: one base pointer, compile-time offsets
+                const C *p = reinterpret_cast<const C *>(line) + t;
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) v[j * R + m] = wok ? __ldcs(p + j * TPL + m * ido) : mk<T>(T(0), T(0));
+            } else if (plain) {
+                const int64_t sa = g.in_sa;
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
 #pragma unroll
@@ -290,6 +310,7 @@ struct Pow2Body {
                 for (int q = 0; q < RL; ++q) {
                     const int k = t + j * TPL + q * (N / RL);
                     C val = mk<T>(v[j * RL + q].y * f, v[j * RL + q].x * f);
+                    if (MODE == 2 && vec) { __stcs(reinterpret_cast<C *>(line + (int64_t)k * 2 * sizeof(T)), val); continue; }
                     if (MODE == 4) {
                         // undo Makhoul's reordering; the sine transform carries (-1)^j
                         const bool lo = k < N / 2;
@@ -309,6 +330,20 @@ struct Pow2Body {
         if (MODE == 0) {
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
+            if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C)) {
+                const T f = g.fct;
+                const bool bw = g.backward != 0;
+                C *p = reinterpret_cast<C *>(line) + t;
+#pragma unroll
+                for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                    for (int q = 0; q < RL; ++q) {
+                        C val = cscale(v[j * RL + q], f);
+                        if (bw) val = cswap(val);
+                        __stcs(p + j * TPL + q * (N / RL), val);
+                    }
+                return;
+            }
             if (g.store_mode == ST_C2C && g.tw_dim < 0) {
                 const T f = g.fct;
                 const bool bw = g.backward != 0;
@@ -355,6 +390,7 @@ struct Pow2Body {
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
             const T half = T(0.5) * g.fct;
             const bool conj_out = g.backward != 0;
+            const bool contig_out = g.out_sa == (int64_t)sizeof(C);
             auto emit = [&](int k) {
                 const C a = sl[k];
                 const C bz = sl[(N - k) & (N - 1)];
@@ -387,8 +423,13 @@ struct Pow2Body {
                     return;
                 }
                 if (conj_out) { x0.y = -x0.y; x1.y = -x1.y; }
-                st_cx<T, true>(line + (int64_t)k * g.out_sa, x0);
-                st_cx<T, true>(line + (int64_t)(N - k) * g.out_sa, x1);
+                if (contig_out) {
+                    __stcs(reinterpret_cast<C *>(line) + k, x0);
+                    __stcs(reinterpret_cast<C *>(line) + (N - k), x1);
+                } else {
+                    st_cx<T, true>(line + (int64_t)k * g.out_sa, x0);
+                    st_cx<T, true>(line + (int64_t)(N - k) * g.out_sa, x1);
+                }
             };
 #pragma unroll
             for (int j = 0; j < 8; ++j) emit(t + j * TPL);

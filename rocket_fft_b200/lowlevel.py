@@ -30,7 +30,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librocketfft_b200.so")
+LIB_PATH = os.environ.get("RFB200_LIB") or os.path.join(_HERE, "librocketfft_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -224,11 +224,8 @@ static bool plan_tile(const LineJob &job, const std::vector<Dim> &dims, TilePlan
     const uint64_t n = job.n;
     const size_t esz = job.prec ? 16 : 8;
     if (n > (1u << 20)) return false;
-    if (n == 1) tp.sched.clear();
-    else {
-        tp.sched = radix_schedule(n, RMAX_GENERIC);
-        if (tp.sched.empty() || tp.sched.size() > (size_t)MAXP) return false;
-    }
+    tp.sched = radix_schedule(n, RMAX_GENERIC);  // n == 1: a single radix-1 pass
+    if (tp.sched.empty() || tp.sched.size() > (size_t)MAXP) return false;
     tp.padsh = (uint32_t)env_int("RFB200_PADSH", job.prec ? 4 : 5);
     uint32_t pitch = (uint32_t)((n - 1) + ((n - 1) >> tp.padsh) + 1);
     pitch |= 1u;
@@ -268,7 +265,7 @@ static void launch_tile_typed(const LineJob &job, const std::vector<Dim> &dims, 
     const uint64_t ntiles = fill_geom<T>(g, job, dims, tp.W, tp.load_lf, tp.store_lf);
     const uint32_t n = (uint32_t)job.n;
     g.npass = (uint32_t)tp.sched.size();
-    uint32_t l1 = 1;
+    uint32_t l1 = 1, twoff = 0;
     for (uint32_t i = 0; i < g.npass; ++i) {
         PassInfo &ps = g.pass[i];
         ps.R = tp.sched[i];
@@ -277,11 +274,14 @@ static void launch_tile_typed(const LineJob &job, const std::vector<Dim> &dims, 
         ps.d_ido = make_fastdiv(ps.ido);
         ps.d_nbl = make_fastdiv(n / ps.R);
         ps.d_R = make_fastdiv(ps.R);
+        ps.twoff = twoff;
+        if (ps.ido > 1) twoff += (ps.R - 1) * ps.ido;
         l1 *= ps.R;
     }
     g.pitch = tp.pitch;
     g.padsh = tp.padsh;
     g.tw = (n > 1) ? (const cx<T> *)get_table(TAB_LINE, job.prec, n, 0) : nullptr;
+    g.ptw = (n > 1) ? (const cx<T> *)get_table(TAB_TILE, job.prec, n, 0) : nullptr;
     auto kern = fft_tile_kernel<T, ALIGNED>;
     static thread_local int dev_set = -1;
     int dev = 0;

@@ -172,12 +172,15 @@ void fill(std::vector<T> &h, TableKind kind, uint64_t n, uint64_t param, size_t 
 // stored at [(q-1)*ido_p + i].  Pass structure as in P2<LOGN> (pow2_kernel.cuh): one radix
 // 2/4/8 pass first when log2 n is not a multiple of 4, then radix-16 passes.
 template <typename T>
-void fill_stockham(std::vector<T> &h, uint64_t n) {
-    int logn = 0;
-    while ((1ull << logn) < n) ++logn;
+void fill_stockham(std::vector<T> &h, uint64_t n, bool tile) {
     std::vector<uint32_t> rad;
-    if (logn % 4) rad.push_back(1u << (logn % 4));
-    for (int i = 0; i < logn / 4; ++i) rad.push_back(16);
+    if (tile) rad = radix_schedule(n, 64);
+    else {
+        int logn = 0;
+        while ((1ull << logn) < n) ++logn;
+        if (logn % 4) rad.push_back(1u << (logn % 4));
+        for (int i = 0; i < logn / 4; ++i) rad.push_back(16);
+    }
     h.clear();
     uint64_t l1 = 1;
     for (auto R : rad) {
@@ -215,19 +218,20 @@ const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool
         case TAB_CHIRP: count = n; break;
         case TAB_CHIRP_FFT: count = param; break;
         case TAB_QUARTER: count = n + 1; break;
-        case TAB_STOCKHAM: count = n; break;  // upper bound: sum (R-1)*ido < n
+        case TAB_STOCKHAM:
+        case TAB_TILE: count = n; break;  // upper bound: sum (R-1)*ido < n
     }
     size_t esz = prec ? 16 : 8;
     void *d = nullptr;
     RFB_CUDA_CHECK(cudaMalloc(&d, count * esz > 0 ? count * esz : esz));
-    if (kind == TAB_STOCKHAM) {
+    if (kind == TAB_STOCKHAM || kind == TAB_TILE) {
         if (prec) {
             std::vector<double> h;
-            fill_stockham(h, n);
+            fill_stockham(h, n, kind == TAB_TILE);
             RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
         } else {
             std::vector<float> h;
-            fill_stockham(h, n);
+            fill_stockham(h, n, kind == TAB_TILE);
             RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
     } else if (kind != TAB_CHIRP_FFT) {

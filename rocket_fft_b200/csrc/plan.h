@@ -30,6 +30,7 @@ enum TableKind : int {
     TAB_CHIRP = 3,     // exp(-i pi t^2 / n), t in [0, n)
     TAB_CHIRP_FFT = 4, // forward DFT_M of the wrapped conjugate chirp, divided by M  (param = M)
     TAB_QUARTER = 5,   // exp(-2 pi i t / (4 n)), t in [0, n]   (DCT/DST and real pre/post factors)
+    TAB_TILE = 7,      // pass-major twiddles of the generic tile kernel for radix_schedule(n, 64)
     TAB_STOCKHAM = 6,  // per-pass twiddles of the power-of-two register kernel (n = 2^k), see pow2_kernel.cuh
 };
 

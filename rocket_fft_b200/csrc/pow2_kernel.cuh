@@ -242,14 +242,20 @@ struct Pow2Body {
 #pragma unroll
                     for (int m = 0; m < R; ++m) v[j * R + m] = wok ? __ldcs(p + j * TPL + m * ido) : mk<T>(T(0), T(0));
             } else if (plain) {
+                // strided line: running pointers instead of a 64-bit multiply per element
                 const int64_t sa = g.in_sa;
+                const int64_t step_m = (int64_t)ido * sa, step_j = (int64_t)TPL * sa;
+                const char *pj = line + (int64_t)t * sa;
 #pragma unroll
-                for (int j = 0; j < NB; ++j)
+                for (int j = 0; j < NB; ++j) {
+                    const char *pm = pj;
 #pragma unroll
                     for (int m = 0; m < R; ++m) {
-                        const int e = t + j * TPL + m * ido;
-                        v[j * R + m] = wok ? *reinterpret_cast<const C *>(line + (int64_t)e * sa) : mk<T>(T(0), T(0));
+                        v[j * R + m] = wok ? *reinterpret_cast<const C *>(pm) : mk<T>(T(0), T(0));
+                        pm += step_m;
                     }
+                    pj += step_j;
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
@@ -344,18 +350,41 @@ struct Pow2Body {
                     }
                 return;
             }
-            if (g.store_mode == ST_C2C && g.tw_dim < 0) {
+            if (g.store_mode == ST_C2C) {
+                // strided output, optionally with the four-step factor exp(-2 pi i c k / bigN):
+                // exact two-level table look-ups for every 4th bin, three recurrence steps between
                 const T f = g.fct;
                 const bool bw = g.backward != 0;
+                const bool tw = g.tw_dim >= 0;
+                const uint32_t c = tw ? ((g.tw_dim == 0) ? (w_first + w) : (g.tw_dim == 1 ? i1 : i2)) : 0u;
+                auto lookup = [&](uint32_t x) {
+                    uint32_t hi, lo;
+                    fdivmod(x, g.d_twS, hi, lo);
+                    return cmul(__ldg(g.twA + hi), __ldg(g.twB + lo));
+                };
+                C step = mk<T>(T(1), T(0));
+                if (tw) step = lookup(c * (uint32_t)(N / RL));
+                const int64_t step_q = (int64_t)(N / RL) * g.out_sa, step_j = (int64_t)TPL * g.out_sa;
+                char *pj = line + (int64_t)t * g.out_sa;
 #pragma unroll
-                for (int j = 0; j < NBL; ++j)
+                for (int j = 0; j < NBL; ++j) {
+                    char *pq = pj;
+                    C wq = mk<T>(T(1), T(0));
 #pragma unroll
                     for (int q = 0; q < RL; ++q) {
-                        const int k = t + j * TPL + q * (N / RL);
-                        C val = cscale(v[j * RL + q], f);
+                        C val = v[j * RL + q];
+                        if (tw) {
+                            if ((q & 3) == 0) wq = lookup(c * (uint32_t)(t + j * TPL + q * (N / RL)));
+                            else wq = cmul(wq, step);
+                            val = cmul(val, wq);
+                        }
+                        val = cscale(val, f);
                         if (bw) val = cswap(val);
-                        *reinterpret_cast<C *>(line + (int64_t)k * g.out_sa) = val;
+                        *reinterpret_cast<C *>(pq) = val;
+                        pq += step_q;
                     }
+                    pj += step_j;
+                }
                 return;
             }
 #pragma unroll

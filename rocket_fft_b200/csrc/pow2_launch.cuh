@@ -8,8 +8,9 @@ namespace rfb {
 
 // lines per CTA: element-fast tiles aim at 256 threads, line-fast tiles at >= 128-byte rows
 constexpr int p2_we(int logn) { return logn <= 10 ? (256 >> (logn - 4)) : (logn == 11 ? 2 : 1); }
+// (measured on B200: 1024-point float lines 8 MiB apart: W=8 -> 2.9 TB/s, W=16 -> 3.7 TB/s)
 constexpr int p2_wl(int logn, bool dbl) {
-    return logn <= 8 ? p2_we(logn) : (logn == 9 ? 16 : (logn == 10 ? 8 : (logn == 11 ? 4 : 0)));
+    return logn <= 8 ? p2_we(logn) : (logn == 9 ? 16 : (logn == 10 ? (dbl ? 8 : 16) : (logn == 11 ? (dbl ? 4 : 8) : 0)));
 }
 
 template <typename T, int LOGN, int W, int MODE>

@@ -1,7 +1,9 @@
 // Generic shared-memory line-FFT kernel: a CTA owns a tile of W lines of length n
-// (any n that fits in shared memory, any factorisation into radices <= 64), runs an
-// in-place decimation-in-frequency pass per factor inside shared memory and undoes the
-// digit reversal while streaming the result out.  Global traffic is exactly one read
+// (any n that fits in shared memory, any factorisation into radices <= 64) and runs one
+// in-place decimation-in-frequency pass per factor.  The FIRST pass reads its butterfly
+// inputs straight from global memory (element i + m*n/R: coalesced) and the LAST pass writes
+// its outputs straight to global memory: thread u computes the butterfly whose outputs are the
+// bins u + q*n/R (coalesced), found through the mixed-radix digit reversal of u.  Global traffic is exactly one read
 // and one write of the tile, coalesced either along the line ("element-fast", lines are
 // contiguous) or across neighbouring lines ("line-fast", lines are strided but the
 // tile's W lines are adjacent in memory -- no transposed copy is ever materialised).
@@ -23,6 +25,7 @@ constexpr int RMAX_GENERIC = 64;  // largest prime radix done as a direct O(R^2)
 
 struct PassInfo {
     uint32_t R, ido, l1;
+    uint32_t twoff;  // offset of this pass's twiddles in the pass-major table ptw
     FastDiv d_ido;   // butterfly -> (k, i)
     FastDiv d_nbl;   // flat butterfly index -> (line, butterfly) ; nbl = n / R
     FastDiv d_R;     // digit extraction for the output permutation
@@ -48,7 +51,8 @@ struct TileGeom {
     FastDiv d_t0, d_e1;              // tile id -> (t0, i1, i2)
     const char *in;
     char *out;
-    const cx<T> *tw;     // exp(-2 pi i t / n), t in [0, n)
+    const cx<T> *tw;     // exp(-2 pi i t / n), t in [0, n)   (roots of the generic-radix butterfly)
+    const cx<T> *ptw;    // pass-major twiddles: pass s, entry [(q-1)*ido + i] = exp(-2 pi i i q / (R ido))
     T fct;
     // optional "four-step" factor on the output: out[k] *= exp(-2 pi i c k / bigN), c the
     // coordinate along batch dim tw_dim; exp(-2 pi i t/bigN) = twA[t / twS] * twB[t % twS]
@@ -59,69 +63,158 @@ struct TileGeom {
 
 __device__ __forceinline__ uint32_t padidx(uint32_t e, uint32_t sh) { return e + (e >> sh); }
 
-template <typename T, int R>
-__device__ __forceinline__ void pass_fixed(cx<T> *buf, const PassInfo &ps, uint32_t W, uint32_t pitch,
-                                           uint32_t padsh, const cx<T> *__restrict__ tw) {
-    using C = cx<T>;
-    const uint32_t ido = ps.ido, l1 = ps.l1;
-    const uint32_t nbl = ps.d_nbl.d;
-    const uint32_t total = W * nbl;
-    for (uint32_t bb = threadIdx.x; bb < total; bb += blockDim.x) {
-        uint32_t w, b, k, i;
-        fdivmod(bb, ps.d_nbl, w, b);
-        fdivmod(b, ps.d_ido, k, i);
-        C *base = buf + (size_t)w * pitch;
-        const uint32_t e0 = i + ido * R * k;
-        C v[R];
-#pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = base[padidx(e0 + ido * m, padsh)];
-        Dft<T, R>::run(v);
-        if (ido > 1 && i > 0) {
-            const uint32_t t = l1 * i;
-#pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + t * q));
+// deliver spectrum bin f (all store modes); line_io.cuh's store_value works by output slot
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void store_bin_value(int mode, int flags, char *line, int64_t sa, uint32_t f, uint32_t n,
+                                                cx<T> val) {
+    switch (mode) {
+        case ST_HALF:
+            if (2 * f > n) return;
+        case ST_C2C: st_cx<T, ALIGNED>(line + (int64_t)f * sa, val); break;
+        case ST_REAL: {
+            T r = val.x;
+            if ((flags & FLAG_NEG_EVEN_OUT) && f >= 2 && !(f & 1)) r = -r;
+            *reinterpret_cast<T *>(line + (int64_t)f * sa) = r;
+            break;
         }
-#pragma unroll
-        for (int q = 0; q < R; ++q) base[padidx(e0 + ido * q, padsh)] = v[q];
+        case ST_HARTLEY: *reinterpret_cast<T *>(line + (int64_t)f * sa) = val.x + val.y; break;
+        case ST_HC:
+            if (2 * f > n) return;
+            if (f == 0) *reinterpret_cast<T *>(line) = val.x;
+            else {
+                *reinterpret_cast<T *>(line + (int64_t)(2 * f - 1) * sa) = val.x;
+                if (2 * f < n) *reinterpret_cast<T *>(line + (int64_t)(2 * f) * sa) = val.y;
+            }
+            break;
     }
 }
 
-// Any radix up to RMAX_GENERIC: O(R^2) butterfly with the roots read from the line table.
-template <typename T>
-__device__ __noinline__ void pass_generic(cx<T> *buf, const PassInfo &ps, uint32_t n, uint32_t W,
-                                          uint32_t pitch, uint32_t padsh, const cx<T> *__restrict__ tw) {
-    using C = cx<T>;
-    const uint32_t R = ps.R, ido = ps.ido, l1 = ps.l1;
-    const uint32_t nbl = ps.d_nbl.d;
-    const uint32_t total = W * nbl;
-    const uint32_t rs = n / R;  // exp(-2 pi i j / R) = tw[j * rs]
-    for (uint32_t bb = threadIdx.x; bb < total; bb += blockDim.x) {
-        uint32_t w, b, k, i;
-        fdivmod(bb, ps.d_nbl, w, b);
-        fdivmod(b, ps.d_ido, k, i);
-        C *base = buf + (size_t)w * pitch;
-        const uint32_t e0 = i + ido * R * k;
-        C v[RMAX_GENERIC], o[RMAX_GENERIC];
-        for (uint32_t m = 0; m < R; ++m) v[m] = base[padidx(e0 + ido * m, padsh)];
-        for (uint32_t q = 0; q < R; ++q) {
+struct TileCtx {
+    uint32_t w_first, wvalid, i1, i2;
+    int64_t in_base, out_base;
+};
+
+// forward DFT of R points in v (natural order in and out); R == 0: runtime radix through roots table
+template <typename T, int R>
+__device__ __forceinline__ void butterfly(cx<T> *v, uint32_t Rr, uint32_t n, const cx<T> *__restrict__ roots) {
+    if constexpr (R != 0) Dft<T, R>::run(v);
+    else {
+        using C = cx<T>;
+        C o[RMAX_GENERIC];
+        const uint32_t rs = n / Rr;
+        for (uint32_t q = 0; q < Rr; ++q) {
             C acc = v[0];
             uint32_t j = 0;
-            for (uint32_t m = 1; m < R; ++m) {
+            for (uint32_t m = 1; m < Rr; ++m) {
                 j += q;
-                if (j >= R) j -= R;
-                C r = __ldg(tw + j * rs);
+                if (j >= Rr) j -= Rr;
+                const C r = __ldg(roots + j * rs);
                 acc.x += v[m].x * r.x - v[m].y * r.y;
                 acc.y += v[m].x * r.y + v[m].y * r.x;
             }
             o[q] = acc;
         }
-        const uint32_t t = l1 * i;
-        base[padidx(e0, padsh)] = o[0];
-        for (uint32_t q = 1; q < R; ++q) {
-            C val = o[q];
-            if (ido > 1 && i > 0) val = cmul(val, __ldg(tw + t * q));
-            base[padidx(e0 + ido * q, padsh)] = val;
+        for (uint32_t q = 0; q < Rr; ++q) v[q] = o[q];
+    }
+}
+
+enum { PASS_FIRST = 0, PASS_MID = 1, PASS_LAST = 2, PASS_ONLY = 3 };
+
+template <typename T, int R, int WHERE, bool ALIGNED>
+__device__ __forceinline__ void run_pass(const TileGeom<T> &g, const TileCtx &cx_, cx<T> *buf, const PassInfo &ps) {
+    using C = cx<T>;
+    constexpr int RA = R ? R : RMAX_GENERIC;
+    const uint32_t Rr = R ? (uint32_t)R : ps.R;
+    const uint32_t n = g.n, W = g.W, pitch = g.pitch, padsh = g.padsh;
+    const uint32_t ido = ps.ido, l1 = ps.l1;
+    const uint32_t nbl = ps.d_nbl.d;
+    const uint32_t total = W * nbl;
+    const bool from_global = (WHERE == PASS_FIRST || WHERE == PASS_ONLY);
+    const bool to_global = (WHERE == PASS_LAST || WHERE == PASS_ONLY);
+    const bool lf = to_global ? (g.store_line_fast != 0) : (from_global ? (g.load_line_fast != 0) : false);
+    for (uint32_t bb = threadIdx.x; bb < total; bb += blockDim.x) {
+        uint32_t w, b;
+        if (lf) fdivmod(bb, g.d_W, b, w);
+        else fdivmod(bb, ps.d_nbl, w, b);
+        C v[RA];
+        uint32_t i, e0, u = b;
+        if (to_global) {
+            // b = u is the low part of the output bin; the butterfly sits at the digit-reversed place
+            uint32_t rem = u, p = 0;
+            for (uint32_t s = 0; s + 1 < g.npass; ++s) {
+                uint32_t q, r;
+                fdivmod(rem, g.pass[s].d_R, q, r);
+                p += r * g.pass[s].ido;
+                rem = q;
+            }
+            i = 0;
+            e0 = p;
+        } else {
+            uint32_t k;
+            fdivmod(b, ps.d_ido, k, i);
+            e0 = i + ido * Rr * k;
         }
+        if (from_global) {
+            const bool ok = w < cx_.wvalid;
+            const char *line = g.in + cx_.in_base + (int64_t)w * g.in_bs[0];
+#pragma unroll
+            for (uint32_t m = 0; m < Rr; ++m) {
+                C val = mk<T>(T(0), T(0));
+                if (ok) {
+                    val = load_value<T, ALIGNED>(g.load_mode, g.flags, line, g.in_sa, e0 + ido * m, n, g.n_in);
+                    if (g.backward) val = cswap(val);
+                }
+                v[m] = val;
+            }
+        } else {
+            const C *base = buf + (size_t)w * pitch;
+#pragma unroll
+            for (uint32_t m = 0; m < Rr; ++m) v[m] = base[padidx(e0 + ido * m, padsh)];
+        }
+        butterfly<T, R>(v, Rr, n, g.tw);
+        if (ido > 1 && i > 0) {
+            const C *tw = g.ptw + ps.twoff + i;
+#pragma unroll
+            for (uint32_t q = 1; q < Rr; ++q) v[q] = cmul(v[q], __ldg(tw + (q - 1) * ido));
+        }
+        if (to_global) {
+            if (w >= cx_.wvalid) continue;
+            char *line = g.out + cx_.out_base + (int64_t)w * g.out_bs[0];
+            const uint32_t c = (g.tw_dim == 0) ? (cx_.w_first + w) : (g.tw_dim == 1 ? cx_.i1 : cx_.i2);
+#pragma unroll
+            for (uint32_t q = 0; q < Rr; ++q) {
+                const uint32_t f = u + l1 * q;
+                C val = v[q];
+                if (g.tw_dim >= 0) {
+                    uint32_t hi, lo;
+                    fdivmod(c * f, g.d_twS, hi, lo);
+                    val = cmul(val, cmul(__ldg(g.twA + hi), __ldg(g.twB + lo)));
+                }
+                val = cscale(val, g.fct);
+                if (g.backward) val = cswap(val);
+                store_bin_value<T, ALIGNED>(g.store_mode, g.flags, line, g.out_sa, f, n, val);
+            }
+        } else {
+            C *base = buf + (size_t)w * pitch;
+#pragma unroll
+            for (uint32_t q = 0; q < Rr; ++q) base[padidx(e0 + ido * q, padsh)] = v[q];
+        }
+    }
+}
+
+template <typename T, int WHERE, bool ALIGNED>
+__device__ __forceinline__ void dispatch_pass(const TileGeom<T> &g, const TileCtx &cx_, cx<T> *buf, const PassInfo &ps) {
+    switch (ps.R) {
+        case 2: run_pass<T, 2, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 3: run_pass<T, 3, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 4: run_pass<T, 4, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 5: run_pass<T, 5, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 7: run_pass<T, 7, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 8: run_pass<T, 8, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 11: run_pass<T, 11, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 13: run_pass<T, 13, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        case 16: run_pass<T, 16, WHERE, ALIGNED>(g, cx_, buf, ps); break;
+        default: run_pass<T, 0, WHERE, ALIGNED>(g, cx_, buf, ps); break;
     }
 }
 
@@ -131,77 +224,26 @@ __global__ void __launch_bounds__(512) fft_tile_kernel(const TileGeom<T> g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
 
-    // ---- which tile -----------------------------------------------------------------
-    uint32_t t0, i1, i2, rest;
+    TileCtx cx_;
+    uint32_t t0, rest;
     fdivmod(blockIdx.x, g.d_t0, rest, t0);
-    fdivmod(rest, g.d_e1, i2, i1);
-    const uint32_t w_first = t0 * g.W;
-    const uint32_t wvalid = min(g.W, g.bext[0] - w_first);
-    const int64_t in_base = (int64_t)w_first * g.in_bs[0] + (int64_t)i1 * g.in_bs[1] + (int64_t)i2 * g.in_bs[2];
-    const int64_t out_base = (int64_t)w_first * g.out_bs[0] + (int64_t)i1 * g.out_bs[1] + (int64_t)i2 * g.out_bs[2];
-    const uint32_t n = g.n, W = g.W, pitch = g.pitch, padsh = g.padsh;
-    const uint32_t tile_elems = W * n;
+    fdivmod(rest, g.d_e1, cx_.i2, cx_.i1);
+    cx_.w_first = t0 * g.W;
+    cx_.wvalid = min(g.W, g.bext[0] - cx_.w_first);
+    cx_.in_base = (int64_t)cx_.w_first * g.in_bs[0] + (int64_t)cx_.i1 * g.in_bs[1] + (int64_t)cx_.i2 * g.in_bs[2];
+    cx_.out_base = (int64_t)cx_.w_first * g.out_bs[0] + (int64_t)cx_.i1 * g.out_bs[1] + (int64_t)cx_.i2 * g.out_bs[2];
 
-    // ---- load ---------------------------------------------------------------------------
-    for (uint32_t idx = threadIdx.x; idx < tile_elems; idx += blockDim.x) {
-        uint32_t w, e;
-        if (g.load_line_fast) fdivmod(idx, g.d_W, e, w);
-        else fdivmod(idx, g.d_n, w, e);
-        C val = mk<T>(T(0), T(0));
-        if (w < wvalid) {
-            val = load_value<T, ALIGNED>(g.load_mode, g.flags, g.in + in_base + (int64_t)w * g.in_bs[0], g.in_sa, e, n,
-                                         g.n_in);
-            if (g.backward) val = cswap(val);
-        }
-        buf[(size_t)w * pitch + padidx(e, padsh)] = val;
+    if (g.npass == 1) {
+        dispatch_pass<T, PASS_ONLY, ALIGNED>(g, cx_, buf, g.pass[0]);
+        return;
     }
+    dispatch_pass<T, PASS_FIRST, ALIGNED>(g, cx_, buf, g.pass[0]);
     __syncthreads();
-
-    // ---- passes -------------------------------------------------------------------------
-    for (uint32_t s = 0; s < g.npass; ++s) {
-        const PassInfo &ps = g.pass[s];
-        switch (ps.R) {
-            case 2: pass_fixed<T, 2>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 3: pass_fixed<T, 3>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 4: pass_fixed<T, 4>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 5: pass_fixed<T, 5>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 7: pass_fixed<T, 7>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 8: pass_fixed<T, 8>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 11: pass_fixed<T, 11>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 13: pass_fixed<T, 13>(buf, ps, W, pitch, padsh, g.tw); break;
-            case 16: pass_fixed<T, 16>(buf, ps, W, pitch, padsh, g.tw); break;
-            default: pass_generic<T>(buf, ps, n, W, pitch, padsh, g.tw); break;
-        }
+    for (uint32_t s = 1; s + 1 < g.npass; ++s) {
+        dispatch_pass<T, PASS_MID, ALIGNED>(g, cx_, buf, g.pass[s]);
         __syncthreads();
     }
-
-    // ---- store (undo the digit reversal on the fly) -------------------------------------
-    const uint32_t n_out = g.n_out;
-    const uint32_t out_elems = W * n_out;
-    for (uint32_t idx = threadIdx.x; idx < out_elems; idx += blockDim.x) {
-        uint32_t w, j;
-        if (g.store_line_fast) fdivmod(idx, g.d_W, j, w);
-        else fdivmod(idx, g.d_nout, w, j);
-        if (w >= wvalid) continue;
-        const uint32_t k = store_bin(g.store_mode, j);
-        uint32_t rem = k, p = 0;
-        for (uint32_t s = 0; s < g.npass; ++s) {
-            uint32_t q, r;
-            fdivmod(rem, g.pass[s].d_R, q, r);
-            p += r * g.pass[s].ido;
-            rem = q;
-        }
-        C val = buf[(size_t)w * pitch + padidx(p, padsh)];
-        if (g.tw_dim >= 0) {
-            const uint32_t c = (g.tw_dim == 0) ? (w_first + w) : (g.tw_dim == 1 ? i1 : i2);
-            uint32_t hi, lo;
-            fdivmod(c * k, g.d_twS, hi, lo);
-            val = cmul(val, cmul(__ldg(g.twA + hi), __ldg(g.twB + lo)));
-        }
-        val = cscale(val, g.fct);
-        if (g.backward) val = cswap(val);
-        store_value<T, ALIGNED>(g.store_mode, g.flags, g.out + out_base + (int64_t)w * g.out_bs[0], g.out_sa, j, val);
-    }
+    dispatch_pass<T, PASS_LAST, ALIGNED>(g, cx_, buf, g.pass[g.npass - 1]);
 }
 
 }  // namespace rfb

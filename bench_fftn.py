@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "symm", "nccl"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "symm", "nccl"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -89,8 +89,14 @@ def main():
     for _ in range(max(3, args.warmup)):
         plan.forward(x, True, 1.0)
     total_ms = timed(lambda: plan.forward(x, True, 1.0), args.steps)
-    a2a_ms = timed(lambda: plan.exchange(x), args.steps)
-    planes_ms = timed(lambda: plan.local_planes(x, True, 1.0), args.steps)
+    if plan.mode == "fused":
+        # the exchange is inside the axis-1 transform: time that kernel pair and, for reference, the
+        # same transform writing locally
+        a2a_ms = timed(lambda: plan.scatter_axis1(x, True), args.steps)  # axis-1 transform + push, one kernel
+        planes_ms = timed(lambda: R.c2c(x, x, [2], True, 1.0), args.steps)  # the other local axis
+    else:
+        a2a_ms = timed(lambda: plan.exchange(x), args.steps)
+        planes_ms = timed(lambda: plan.local_planes(x, True, 1.0), args.steps)
     pack_ms = timed(lambda: plan.pack(x), args.steps) if plan.mode == "nccl" else 0.0
     axis0_ms = timed(lambda: plan.local_axis0(True), args.steps)
     # parity: inverse transform brings the data back
@@ -110,7 +116,8 @@ def main():
                           "alltoall_frac_of_900": bus / 900.0, "alltoall_frac_of_measured_770": bus / 770.0,
                           "bytes_sent_per_gpu": plan.bytes_sent_per_rank,
                           "stages_ms": {"local_planes": planes_ms, "pack": pack_ms, "alltoall": a2a_ms, "axis0": axis0_ms},
-                          "exchange": plan.mode + (" (pack fused into the push)" if plan.mode == "symm" else " (pack + all_to_all_single; alltoall_ms includes the pack)"),
+                          "exchange": plan.mode + {"symm": " (pack fused into the push)", "nccl": " (pack + all_to_all_single; alltoall_ms includes the pack)",
+                                                   "fused": " (axis-1 FFT kernel stores straight into peer HBM; alltoall_ms = that kernel incl. its butterflies)"}[plan.mode],
                           "layout": "result left axis-1 sharded (transposed); transpose_back available",
                           "parseval_rel_err": parseval}))
     dist.destroy_process_group()

@@ -107,6 +107,16 @@ int rfb200_r2r_genuine_hartley(int precision, size_t ndim, const int64_t *shape,
                                size_t naxes, const uint64_t *axes, double fct, const void *d_in,
                                void *d_out, void *stream);
 
+/* c2c along ONE axis with the output axis scattered: output index k along `axis` (extent n) is
+ * cut into `nparts` equal blocks and block h is written to d_out_parts[h] -- an array shaped like
+ * `shape` with the axis extent n/nparts, addressed with stride_out -- which may live on a PEER GPU
+ * (NVLink-mapped pointer): the local transform and the all-to-all push of a slab-decomposed N-D
+ * transform happen in one kernel.  Needs a power-of-two axis length (16..16384).  No reference
+ * counterpart (the reference is single-process). */
+int rfb200_c2c_scatter(int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+                       const int64_t *stride_out, size_t axis, int forward, double fct,
+                       const void *d_in, size_t nparts, void *const *d_out_parts, void *stream);
+
 /* ---- housekeeping ----------------------------------------------------------------- */
 /* Last error message of the calling thread ("" if none); cleared by rfb200_clear_error. */
 const char *rfb200_last_error(void);

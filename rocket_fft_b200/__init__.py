@@ -4,6 +4,7 @@ from .lowlevel import (  # noqa: F401
     LIB_PATH,
     TransformError,
     c2c,
+    c2c_scatter,
     c2c_sym,
     c2r,
     dct,

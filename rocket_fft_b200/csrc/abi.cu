@@ -265,6 +265,32 @@ RFB_EXPORT int rfb200_r2r_genuine_hartley(DEV_ARGS, double fct, const void *d_in
     return run_device_op(OP_GEN_HARTLEY, DEV_PASS, fct, d_in, d_out, stream, mk_flags(true));
 }
 
+RFB_EXPORT int rfb200_c2c_scatter(int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+                                  const int64_t *stride_out, size_t axis, int forward, double fct, const void *d_in,
+                                  size_t nparts, void *const *d_out_parts, void *stream) {
+    clear_error();
+    try {
+        NdArgs a;
+        a.prec = precision ? 1 : 0;
+        a.shape.assign(shape, shape + ndim);
+        a.sin.assign(stride_in, stride_in + ndim);
+        a.sout.assign(stride_out, stride_out + ndim);
+        a.in = (const char *)d_in;
+        a.out = nullptr;
+        a.fct = fct;
+        if (axis >= ndim) { set_error("axis out of range"); throw Error(); }
+        std::vector<char *> parts;
+        for (size_t i = 0; i < nparts; ++i) parts.push_back((char *)d_out_parts[i]);
+        op_c2c_scatter(a, axis, forward != 0, parts, (cudaStream_t)stream);
+        return 0;
+    } catch (const Error &) {
+        return 1;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return 1;
+    }
+}
+
 // ---- housekeeping ---------------------------------------------------------------------------------
 RFB_EXPORT const char *rfb200_last_error(void) { return rfb::last_error(); }
 RFB_EXPORT void rfb200_clear_error(void) { rfb::clear_error(); }

@@ -212,6 +212,7 @@ static bool alignment_ok(const LineJob &job, const std::vector<Dim> &dims) {
         a = a && ok((int64_t)(uintptr_t)job.in) && ok(job.is);
         for (auto &d : dims) a = a && ok(d.is);
     }
+    for (auto ptr : job.split_out) a = a && ok((int64_t)(uintptr_t)ptr);
     if (cout) {
         a = a && ok((int64_t)(uintptr_t)job.out) && ok(job.os);
         for (auto &d : dims) a = a && ok(d.os);
@@ -427,6 +428,10 @@ static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStrea
         const bool done = job.prec ? launch_pow2_f64(job, dims, load_lf, store_lf, s)
                                    : launch_pow2_f32(job, dims, load_lf, store_lf, s);
         if (done) return;
+    }
+    if (!job.split_out.empty()) {
+        set_error("scatter output needs a power-of-two axis length between 16 and 16384 and aligned arrays");
+        throw Error();
     }
     TilePlan tp;
     bool tile_ok = plan_tile(job, dims, tp);

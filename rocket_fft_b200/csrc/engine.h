@@ -31,6 +31,10 @@ struct LineJob {
     int flags = 0;
     uint64_t n_in = 0;   // input elements present per line (0: n); the rest is zero padding
     uint64_t twN = 0;    // four-step factor exp(-2 pi i c k / twN) on the output (0: none)
+    // scatter: output bin k goes to split_out[k / split_blk] (a base pointer already adjusted so that
+    // the usual offset arithmetic with the full index k applies); empty: everything goes to `out`
+    std::vector<char *> split_out;
+    uint64_t split_blk = 0;
 };
 
 void run_lines(const LineJob &job, cudaStream_t stream);
@@ -48,6 +52,9 @@ struct NdArgs {
 };
 
 void op_c2c(const NdArgs &a, bool forward, cudaStream_t s);
+// c2c along ONE axis whose output index is cut into parts.size() equal blocks, block h written to
+// parts[h] (arrays of shape `shape` with the axis extent divided by the number of parts)
+void op_c2c_scatter(const NdArgs &a, size_t axis, bool forward, const std::vector<char *> &parts, cudaStream_t s);
 void op_r2c(const NdArgs &a, bool forward, cudaStream_t s);      // shape = real input shape
 void op_c2r(const NdArgs &a, bool forward, cudaStream_t s);      // shape = real output shape
 void op_c2c_sym(const NdArgs &a, bool forward, cudaStream_t s);

@@ -52,6 +52,12 @@ inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<
     if (ntiles >= (1ull << 31)) { set_error("too many tiles in one launch"); throw Error(); }
     g.in = job.in;
     g.out = job.out;
+    if (!job.split_out.empty()) {
+        if (job.split_out.size() > 16) { set_error("at most 16 scatter destinations"); throw Error(); }
+        g.split_blk = (uint32_t)job.split_blk;
+        g.d_split = make_fastdiv(g.split_blk);
+        for (size_t i = 0; i < job.split_out.size(); ++i) g.split_base[i] = job.split_out[i];
+    }
     g.fct = (T)job.fct;
     if (g.tw_dim >= 0) {
         const uint32_t S = split_size(job.twN);

@@ -78,6 +78,28 @@ void op_c2c(const NdArgs &a, bool forward, cudaStream_t s) {
     c2c_axes(a.prec, a.shape, a.sin, a.sout, a.axes.data(), a.axes.size(), a.in, a.out, forward, a.fct, s);
 }
 
+// c2c along one axis with the output axis scattered over several buffers (the fused
+// "local transform + all-to-all push" of the slab-decomposed fftn; no reference counterpart)
+void op_c2c_scatter(const NdArgs &a, size_t axis, bool forward, const std::vector<char *> &parts, cudaStream_t s) {
+    if (any_zero(a.shape)) return;
+    const uint64_t n = (uint64_t)a.shape[axis];
+    if (parts.empty() || n % parts.size()) { set_error("axis length must be divisible by the number of parts"); throw Error(); }
+    LineJob j;
+    j.prec = a.prec;
+    j.n = n;
+    j.in = a.in;
+    j.out = nullptr;
+    j.is = a.sin[axis];
+    j.os = a.sout[axis];
+    j.batch = batch_dims(a.shape, a.sin, a.sout, axis);
+    j.backward = !forward;
+    j.fct = a.fct;
+    j.split_blk = n / parts.size();
+    for (size_t h = 0; h < parts.size(); ++h)
+        j.split_out.push_back(parts[h] - (int64_t)(h * j.split_blk) * a.sout[axis]);
+    run_lines(j, s);
+}
+
 // ---------------------------------------------------------------------------------------
 // r2c  (reference: r2c H:3955-3975: real transform along axes.back(), then c2c in place on
 // the half-spectrum array over the remaining axes, fct applied by the real transform)

@@ -336,7 +336,7 @@ struct Pow2Body {
         if (MODE == 0) {
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
-            if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C)) {
+            if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C) && g.split_blk == 0) {
                 const T f = g.fct;
                 const bool bw = g.backward != 0;
                 C *p = reinterpret_cast<C *>(line) + t;
@@ -380,7 +380,12 @@ struct Pow2Body {
                         }
                         val = cscale(val, f);
                         if (bw) val = cswap(val);
-                        *reinterpret_cast<C *>(pq) = val;
+                        if (g.split_blk) {
+                            // fused exchange: the bin's block decides which (peer) buffer receives it
+                            const uint32_t k = (uint32_t)(t + j * TPL + q * (N / RL));
+                            char *dst = g.split_base[fdiv(k, g.d_split)] + (pq - g.out);
+                            *reinterpret_cast<C *>(dst) = val;
+                        } else *reinterpret_cast<C *>(pq) = val;
                         pq += step_q;
                     }
                     pj += step_j;

@@ -59,6 +59,10 @@ struct TileGeom {
     int tw_dim;          // -1: none
     FastDiv d_twS;
     const cx<T> *twA, *twB;
+    // scatter of the output axis over several destination buffers (peer GPUs): bin k -> split_base[k / split_blk]
+    uint32_t split_blk;  // 0: off
+    FastDiv d_split;
+    char *split_base[16];
 };
 
 __device__ __forceinline__ uint32_t padidx(uint32_t e, uint32_t sh) { return e + (e >> sh); }

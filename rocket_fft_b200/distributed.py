@@ -49,6 +49,7 @@ class SlabFFTN:
         self.shape = (n0, n1, n2)
         self.dtype = dtype
         self.device = device
+        local_c2c_is_default = local_c2c is None
         if local_c2c is None:
             from . import lowlevel
 
@@ -59,13 +60,15 @@ class SlabFFTN:
         self.local_out_shape = (n0, n1 // P, n2)
         blk = (P, n0 // P, n1 // P, n2)
         self.bytes_sent_per_rank = n0 // P * n1 * n2 * torch.empty((), dtype=dtype).element_size() * (P - 1) // P
-        # Exchange engine.  "symm": peer-mapped symmetric receive buffers (torch symmetric memory
+        # Exchange engine.  "fused": symm buffers + the axis-1 transform writes its output
+        # straight into the peers' receive buffers (rfb200_c2c_scatter): transform and all-to-all
+        # are ONE kernel, the NVLink traffic overlaps the butterflies.  "symm": peer-mapped symmetric receive buffers (torch symmetric memory
         # over NVLink P2P): every rank PUSHES its strided blocks straight into the peers' receive
         # buffers -- the pack pass disappears and no NCCL staging is involved.  "nccl": pack +
         # all_to_all_single.  "auto": symm on CUDA when it can be set up, else nccl.
         self.mode = "nccl"
         self.hdl = None
-        if exchange in ("auto", "symm") and str(device).startswith("cuda"):
+        if exchange in ("auto", "symm", "fused") and str(device).startswith("cuda"):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
 
@@ -75,8 +78,13 @@ class SlabFFTN:
                 self.peer_recv = [self.hdl.get_buffer(h, blk, dtype) for h in range(P)]
                 self.streams = [torch.cuda.Stream(device=device) for _ in range(min(P, 4))]
                 self.mode = "symm"
+                n1_ok = (n1 & (n1 - 1)) == 0 and 16 <= n1 <= 16384
+                if exchange == "fused" or (exchange == "auto" and n1_ok and local_c2c_is_default):
+                    if not n1_ok:
+                        raise ValueError("fused exchange needs a power-of-two axis-1 length (16..16384)")
+                    self.mode = "fused"
             except Exception as e:  # pragma: no cover - depends on the box
-                if exchange == "symm":
+                if exchange in ("symm", "fused"):
                     raise
                 self.symm_error = repr(e)
                 self.hdl = None
@@ -100,6 +108,8 @@ class SlabFFTN:
 
     def exchange(self, x=None):
         """Move block (g -> h) for all h.  symm mode reads the strided slab `x` directly."""
+        if self.mode == "fused":
+            raise RuntimeError("fused mode has no stand-alone exchange (it is part of the axis-1 transform)")
         if self.mode == "nccl":
             if x is not None:
                 self.pack(x)
@@ -124,6 +134,21 @@ class SlabFFTN:
         self.hdl.barrier(channel=1)  # everybody's pushes have landed
         return self.recv
 
+    def planes_and_exchange_fused(self, x, forward=True, fct=1.0):
+        """Axis-2 transform in place, then the axis-1 transform whose stores land in the peers'
+        receive buffers (one kernel = transform + all-to-all push over NVLink)."""
+        self.c2c(x, x, [2], forward, fct)
+        return self.scatter_axis1(x, forward)
+
+    def scatter_axis1(self, x, forward=True):
+        from . import lowlevel
+
+        self.hdl.barrier(channel=0)  # peers are done reading their receive buffers
+        parts = [self.peer_recv[h][self.rank] for h in range(self.P)]
+        lowlevel.c2c_scatter(x, parts, 1, forward, 1.0)
+        self.hdl.barrier(channel=1)  # everybody's pushes have landed
+        return self.recv
+
     def local_axis0(self, forward=True):
         """recv viewed as (n0, n1/P, n2): transform along axis 0 in place."""
         y = self.recv.view(self.local_out_shape)
@@ -133,8 +158,11 @@ class SlabFFTN:
     def forward(self, x, forward=True, fct=1.0, transpose_back=False):
         """x: this rank's slab (n0/P, n1, n2), overwritten.  Returns the local part of the
         result: (n0, n1/P, n2) [axis-1 sharded] or, with transpose_back, (n0/P, n1, n2)."""
-        self.local_planes(x, forward, fct)
-        self.exchange(x)
+        if self.mode == "fused":
+            self.planes_and_exchange_fused(x, forward, fct)
+        else:
+            self.local_planes(x, forward, fct)
+            self.exchange(x)
         y = self.local_axis0(forward)
         if not transpose_back:
             return y

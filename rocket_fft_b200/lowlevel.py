@@ -216,6 +216,34 @@ def r2r_fftpack(ain, aout, axes, real2hermitian, forward, fct, nthreads=1):
     )
 
 
+_c.rfb200_c2c_scatter.restype = C.c_int
+_c.rfb200_c2c_scatter.argtypes = [C.c_int, C.c_size_t, _I64P, _I64P, _I64P, C.c_size_t, C.c_int, C.c_double,
+                                  C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+
+
+def c2c_scatter(ain, parts, axis, forward, fct):
+    """c2c along `axis` of the device array `ain`; the output index along that axis is cut into
+    len(parts) equal blocks and block h is written into parts[h] (device arrays, possibly
+    peer-mapped, all with the same strides and the axis extent n/len(parts))."""
+    pin, shp, st_in, _, dev_in, _k = _abi.describe(ain)
+    if not dev_in:
+        raise TypeError("c2c_scatter works on device arrays")
+    prec = 0 if _abi.dtype_of(ain) == np.dtype(np.complex64) else 1
+    nd = len(shp)
+    desc = [_abi.describe(p) for p in parts]
+    st_out = desc[0][2]
+    for d in desc:
+        if d[2] != st_out or not d[4]:
+            raise ValueError("all parts must be device arrays with identical strides")
+    A = (C.c_int64 * nd)
+    ptrs = (C.c_void_p * len(parts))(*[d[0] for d in desc])
+    rc = _c.rfb200_c2c_scatter(prec, nd, A(*shp), A(*st_in), A(*st_out), int(axis) % nd, int(bool(forward)), float(fct),
+                               C.c_void_p(pin), len(parts), ptrs, C.c_void_p(_current_stream()))
+    if rc != 0:
+        raise TransformError(last_error())
+    return parts
+
+
 def good_size(n, real):
     return lib.good_size(n, real)
 

@@ -21,7 +21,8 @@ for shape in ((128, 128, 128), (64, 96, 40)):
     full = torch.randn(*shape, dtype=torch.complex64, device=dev, generator=g)  # same on every rank
     lo, hi = shard_batch(shape[0], rank, world)
     x = full[lo:hi].clone()
-    plan = SlabFFTN(shape, torch.complex64, dev)
+    plan = SlabFFTN(shape, torch.complex64, dev, exchange="fused" if shape[1] == 128 else "symm")
+    print(f"rank {rank} exchange mode {plan.mode}", flush=True)
     y = plan.forward(x, True, 1.0)
     want = torch.fft.fftn(full)
     j0, j1 = shard_batch(shape[1], rank, world)

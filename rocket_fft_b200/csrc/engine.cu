@@ -255,7 +255,8 @@ static bool plan_tile(const LineJob &job, const std::vector<Dim> &dims, TilePlan
     tp.W = (uint32_t)W;
     tp.smem = (size_t)W * line_bytes;
     uint64_t work = W * n;
-    uint32_t th = (uint32_t)std::min<uint64_t>(512, std::max<uint64_t>(64, ((work / 4 + 31) / 32) * 32));
+    const uint64_t max_th = job.prec ? 512 : 1024;
+    uint32_t th = (uint32_t)std::min<uint64_t>(max_th, std::max<uint64_t>(64, ((work / 4 + 31) / 32) * 32));
     tp.threads = th;
     return true;
 }
@@ -583,8 +584,8 @@ static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cuda
             RFB_CUDA_CHECK(cudaStreamSynchronize(s));
         }
     }
-    // process the lines in chunks so the padded work area stays bounded (<= ~2 GiB)
-    const uint64_t max_lines = std::max<uint64_t>(1, (2ull << 30) / (M * esz));
+    // process the lines in chunks so the padded work area stays bounded (<= ~6 GiB)
+    const uint64_t max_lines = std::max<uint64_t>(1, (6ull << 30) / (M * esz));
     if (L > max_lines && dims.size() >= 1) {
         // split along the outermost batch dim
         std::vector<Dim> inner(dims.begin(), dims.end() - 1);

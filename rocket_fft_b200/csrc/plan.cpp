@@ -92,6 +92,12 @@ std::vector<uint32_t> radix_schedule(uint64_t n, uint32_t rmax) {
         if (rem == 2) sched.push_back(4);
         if (rem == 3) sched.push_back(8);
     }
+    // odd primes ascending, except that the largest one leads: the first pass reads global memory
+    // (more independent loads per butterfly) and the last one writes it (fewer digit reversals)
+    if (odd.size() > 2) {
+        sched.push_back(odd.back());
+        odd.pop_back();
+    }
     for (auto p : odd) sched.push_back(p);
     if (sched.empty()) sched.push_back(1);  // n == 1
     return sched;

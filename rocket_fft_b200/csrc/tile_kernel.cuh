@@ -222,8 +222,12 @@ __device__ __forceinline__ void dispatch_pass(const TileGeom<T> &g, const TileCt
     }
 }
 
+// float tiles run with up to 1024 threads (one big tile per SM needs the warps to hide latency),
+// double tiles with up to 512 (register budget of the radix-16 butterfly)
+template <typename T> constexpr int tile_max_threads() { return sizeof(T) == 4 ? 1024 : 512; }
+
 template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(512) fft_tile_kernel(const TileGeom<T> g) {
+__global__ void __launch_bounds__(tile_max_threads<T>()) fft_tile_kernel(const TileGeom<T> g) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);

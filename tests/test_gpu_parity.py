@@ -409,3 +409,30 @@ def test_numba_njit_calls_run_on_the_gpu(R):
     jit_hartley(a, out, np.arange(2), 1.0, 1)
     w = np.fft.fftn(a)
     check(out, w.real + w.imag, np.float64, a.size, "hartley")
+
+
+def test_reentrancy_many_python_threads(R):
+    """The reference's tests/test_multithreading.py pattern: concurrent calls from 8 threads
+    (here with the results actually checked)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = np.random.default_rng(9)
+    arrays = [cplx(rng, (4, 2**14), np.complex128) for _ in range(24)]
+    reals = [rng.standard_normal((3, 1000)) for _ in range(24)]
+
+    def work(i):
+        x = arrays[i]
+        out = np.empty_like(x)
+        R.c2c(x, out, [1], True, 1.0)
+        e1 = parity.l2err(out, np.fft.fft(x, axis=1))
+        r = reals[i]
+        d = np.empty_like(r)
+        R.dct(r, d, [1], 2, 1.0, False)
+        import scipy.fft
+
+        e2 = parity.l2err(d, scipy.fft.dct(r, 2, axis=1))
+        return max(e1, e2)
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        errs = list(ex.map(work, range(24)))
+    assert max(errs) < 1e-12, errs

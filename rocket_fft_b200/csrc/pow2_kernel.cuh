@@ -133,7 +133,7 @@ struct Pow2Body {
             constexpr int R = PL::radix(0), NB = 16 / R, ido = PL::ido(0);
             int w, t;
             map(lf_in, tid, w, t);
-            const bool wok = w < wvalid;
+            const bool wok = (W == 1) ? true : (w < wvalid);  // W == 1: the grid has exactly one CTA per line
             const char *line = g.in + in_base + (int64_t)w * g.in_bs[0];
             // All 16 loads are issued back to back with nothing depending on them in between
             // (memory-level parallelism: 16 independent requests per thread in flight).

@@ -434,6 +434,16 @@ static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStrea
         set_error("scatter output needs a power-of-two axis length between 16 and 16384 and aligned arrays");
         throw Error();
     }
+    if (job.pre_tab || job.post_tab) {
+        // fused factors exist only in the power-of-two kernel: long (or strided long) lines split first
+        uint64_t a, b;
+        if (job.twN == 0 && job.g_mul == 1 && choose_split(job.n, job.prec, a, b)) {
+            run_fourstep(job, dims, s);
+            return;
+        }
+        set_error("internal: fused element-wise factors need the power-of-two kernel");
+        throw Error();
+    }
     TilePlan tp;
     bool tile_ok = plan_tile(job, dims, tp);
     if (tile_ok && simple && (tp.load_lf || tp.store_lf) && job.twN == 0) {
@@ -533,6 +543,12 @@ static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaS
     A.fct = 1.0;
     A.load_mode = job.load_mode;
     A.twN = job.n;
+    if (job.pre_tab) {  // global element index j1*n2 + j0
+        A.pre_tab = job.pre_tab;
+        A.pre_bound = job.pre_bound;
+        A.pre_swap = job.pre_swap;
+        A.g_mul = n2;
+    }
     run_lines(A, s);
     // B: for every k1 an n2-point DFT over j0 of scratch[k1*n2 + j0] -> X[k2*n1 + k1]
     LineJob B;
@@ -541,11 +557,17 @@ static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaS
     B.is = s_axis;
     B.os = (int64_t)n1 * job.os;
     for (size_t i = 0; i < dims.size(); ++i) B.batch.push_back(Dim{dims[i].n, sstr[i], dims[i].os, false});
-    B.batch.push_back(Dim{(int64_t)n1, (int64_t)n2 * s_axis, job.os, false});
+    B.batch.push_back(Dim{(int64_t)n1, (int64_t)n2 * s_axis, job.os, job.post_tab != nullptr});
     B.in = (const char *)sc.p;
     B.out = job.out;
     B.backward = job.backward;
     B.fct = job.fct;
+    if (job.post_tab) {  // global bin k2*n1 + k1
+        B.post_tab = job.post_tab;
+        B.post_bound = job.post_bound;
+        B.post_swap = job.post_swap;
+        B.g_mul = n1;
+    }
     run_lines(B, s);
 }
 
@@ -582,6 +604,61 @@ static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cuda
             f.out = (char *)w;
             run_lines(f, s);
             RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+    }
+    // ---- fused pipeline: two FFT_M jobs, chirp / padding / spectrum multiply / truncation ride on
+    //      their loads and stores (needs the power-of-two kernel for every launch) ----------------
+    {
+        int logM = 0;
+        while ((1ull << logM) < M) ++logM;
+        bool fusable = alignment_ok(job, dims) && env_int("RFB200_NO_FUSED_BLUESTEIN", 0) == 0 && logM >= 4;
+        if (M > 2048) fusable = fusable && logM <= 22 && dims.size() + 1 <= (size_t)MAXB;
+        else fusable = fusable && dims.size() <= (size_t)MAXB;
+        const uint64_t max_lines_f = std::max<uint64_t>(1, (8ull << 30) / (M * esz));
+        if (fusable && L <= max_lines_f) {
+            const bool lf = !dims.empty() && (iabs64(dims[0].is) < iabs64(job.is) || iabs64(dims[0].os) < iabs64(job.os));
+            std::vector<int64_t> sstr(dims.size());
+            int64_t s_axis, acc;
+            if (lf) {
+                sstr[0] = (int64_t)esz;
+                s_axis = dims[0].n * (int64_t)esz;
+                acc = s_axis * (int64_t)M;
+                for (size_t i = 1; i < dims.size(); ++i) { sstr[i] = acc; acc *= dims[i].n; }
+            } else {
+                s_axis = (int64_t)esz;
+                acc = (int64_t)(M * esz);
+                for (size_t i = 0; i < dims.size(); ++i) { sstr[i] = acc; acc *= dims[i].n; }
+            }
+            Scratch s1(L * M * esz, s);
+            LineJob f;
+            f.prec = job.prec;
+            f.n = M;
+            f.is = job.is;
+            f.os = s_axis;
+            for (size_t i = 0; i < dims.size(); ++i) f.batch.push_back(Dim{dims[i].n, dims[i].is, sstr[i], false});
+            f.in = job.in;
+            f.out = (char *)s1.p;
+            f.pre_tab = chirp;
+            f.pre_bound = n;
+            f.pre_swap = job.backward;
+            f.post_tab = bhat;
+            f.post_bound = M;
+            run_lines(f, s);
+            LineJob b;
+            b.prec = job.prec;
+            b.n = M;
+            b.is = s_axis;
+            b.os = job.os;
+            for (size_t i = 0; i < dims.size(); ++i) b.batch.push_back(Dim{dims[i].n, sstr[i], dims[i].os, false});
+            b.in = (const char *)s1.p;
+            b.out = job.out;
+            b.backward = true;
+            b.fct = job.fct;
+            b.post_tab = chirp;
+            b.post_bound = n;
+            b.post_swap = job.backward;
+            run_lines(b, s);
+            return;
         }
     }
     // process the lines in chunks so the padded work area stays bounded (<= ~6 GiB)

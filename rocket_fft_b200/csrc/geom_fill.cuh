@@ -33,11 +33,13 @@ inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<
     g.in_sa = job.is;
     g.out_sa = job.os;
     g.tw_dim = -1;
+    g.c_dim = -1;
     for (int d = 0; d < MAXB; ++d) {
         if (d < (int)dims.size()) {
             g.bext[d] = (uint32_t)dims[d].n;
             g.in_bs[d] = dims[d].is;
             g.out_bs[d] = dims[d].os;
+            if (dims[d].tw) g.c_dim = d;
             if (dims[d].tw && job.twN) g.tw_dim = d;
         } else {
             g.bext[d] = 1;
@@ -52,6 +54,13 @@ inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<
     if (ntiles >= (1ull << 31)) { set_error("too many tiles in one launch"); throw Error(); }
     g.in = job.in;
     g.out = job.out;
+    g.g_mul = (uint32_t)job.g_mul;
+    g.pre_tab = (const cx<T> *)job.pre_tab;
+    g.post_tab = (const cx<T> *)job.post_tab;
+    g.pre_bound = (uint32_t)job.pre_bound;
+    g.post_bound = (uint32_t)job.post_bound;
+    g.pre_swap = job.pre_swap ? 1 : 0;
+    g.post_swap = job.post_swap ? 1 : 0;
     if (!job.split_out.empty()) {
         if (job.split_out.size() > 16) { set_error("at most 16 scatter destinations"); throw Error(); }
         g.split_blk = (uint32_t)job.split_blk;

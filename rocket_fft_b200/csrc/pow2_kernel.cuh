@@ -234,6 +234,32 @@ struct Pow2Body {
                         v[idx] = cswap(mk<T>(s.x - wd.y, s.y + wd.x));
                     }
                 }
+            } else if (MODE == 0 && g.pre_tab != nullptr) {
+                // zero-padded load with a fused element-wise factor (Bluestein's chirp): global index
+                // gi = e * g_mul + c decides both the padding and the table entry
+                const uint32_t c = g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2));
+                const int64_t sa = g.in_sa;
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const uint32_t e = (uint32_t)(t + j * TPL + m * ido);
+                        const uint32_t gi = e * g.g_mul + c;
+                        const bool ok = wok && gi < g.pre_bound;
+                        v[j * R + m] = ok ? *reinterpret_cast<const C *>(line + (int64_t)e * sa) : mk<T>(T(0), T(0));
+                    }
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const uint32_t e = (uint32_t)(t + j * TPL + m * ido);
+                        const uint32_t gi = e * g.g_mul + c;
+                        if (gi < g.pre_bound) {
+                            C val = v[j * R + m];
+                            if (g.pre_swap) val = cswap(val);
+                            v[j * R + m] = cmul(val, __ldg(g.pre_tab + gi));
+                        }
+                    }
             } else if (packed_vec || (plain && g.in_sa == (int64_t)sizeof(C))) {
                 // contiguous line: one base pointer, compile-time offsets
                 const C *p = reinterpret_cast<const C *>(line) + t;
@@ -336,7 +362,8 @@ struct Pow2Body {
         if (MODE == 0) {
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
-            if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C) && g.split_blk == 0) {
+            if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C) && g.split_blk == 0 &&
+                g.post_tab == nullptr) {
                 const T f = g.fct;
                 const bool bw = g.backward != 0;
                 C *p = reinterpret_cast<C *>(line) + t;
@@ -380,6 +407,14 @@ struct Pow2Body {
                         }
                         val = cscale(val, f);
                         if (bw) val = cswap(val);
+                        if (g.post_tab != nullptr) {
+                            // fused element-wise factor / truncation on the way out (Bluestein)
+                            const uint32_t cc = g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2));
+                            const uint32_t bin = (uint32_t)(t + j * TPL + q * (N / RL)) * g.g_mul + cc;
+                            if (bin >= g.post_bound) { pq += step_q; continue; }
+                            val = cmul(val, __ldg(g.post_tab + bin));
+                            if (g.post_swap) val = cswap(val);
+                        }
                         if (g.split_blk) {
                             // fused exchange: the bin's block decides which (peer) buffer receives it
                             const uint32_t k = (uint32_t)(t + j * TPL + q * (N / RL));

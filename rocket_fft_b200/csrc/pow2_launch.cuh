@@ -110,6 +110,7 @@ bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load
         n /= 2;
     } else if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
     if (!job.split_out.empty() && (mode != 0 || job.store_mode != ST_C2C)) return false;
+    if ((job.pre_tab || job.post_tab) && (mode != 0 || job.store_mode != ST_C2C || job.load_mode != LD_C2C)) return false;
     if (n < 16 || (n & (n - 1))) return false;
     int logn = 0;
     while ((1ull << logn) < n) ++logn;

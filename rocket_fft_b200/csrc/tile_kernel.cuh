@@ -63,6 +63,11 @@ struct TileGeom {
     uint32_t split_blk;  // 0: off
     FastDiv d_split;
     char *split_base[16];
+    // fused element-wise factors (power-of-two kernel only), see LineJob
+    int c_dim;           // batch dim whose coordinate enters g = e * g_mul + c (-1: c = 0)
+    uint32_t g_mul, pre_bound, post_bound;
+    const cx<T> *pre_tab, *post_tab;
+    int pre_swap, post_swap;
 };
 
 __device__ __forceinline__ uint32_t padidx(uint32_t e, uint32_t sh) { return e + (e >> sh); }

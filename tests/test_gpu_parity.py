@@ -436,3 +436,31 @@ def test_reentrancy_many_python_threads(R):
     with ThreadPoolExecutor(max_workers=8) as ex:
         errs = list(ex.map(work, range(24)))
     assert max(errs) < 1e-12, errs
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_bluestein_strided_and_batched(R, dt):
+    """Prime lengths > 64 (chirp-z) along contiguous and strided axes, forward and backward,
+    in place and with fct -- exercises the fused chirp/pad/multiply/truncate paths."""
+    T = trusted()
+    rng = np.random.default_rng(10)
+    cdt = CD[dt]
+    for shp, axes in (((67, 5, 3), [0]), ((131, 4), [0]), ((6, 4099), [1]), ((3, 2, 257), [2]), ((521, 33), [0, 1]),
+                      ((2, 70001), [1]), ((70001, 2), [0])):
+        x = cplx(rng, shp, cdt)
+        n = int(np.prod([shp[a] for a in axes]))
+        for fwd in (True, False):
+            a, b = np.empty_like(x), np.empty_like(x)
+            R.c2c(x, a, axes, fwd, 0.75)
+            T.c2c(x, b, axes, fwd, 0.75)
+            check(a, b, dt, n, (shp, axes, fwd))
+        y = x.copy()
+        R.c2c(y, y, axes, True, 1.0)
+        T.c2c(x, b, axes, True, 1.0)
+        check(y, b, dt, n, (shp, axes, "in place"))
+    xr = rng.standard_normal((4, 4099)).astype(dt)
+    a = np.zeros((4, 2050), dtype=cdt)
+    b = np.zeros_like(a)
+    R.r2c(xr, a, [1], True, 1.0)
+    T.r2c(xr, b, [1], True, 1.0)
+    check(a, b, dt, 4099, "r2c prime")

@@ -434,6 +434,13 @@ static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStrea
         set_error("scatter output needs a power-of-two axis length between 16 and 16384 and aligned arrays");
         throw Error();
     }
+    // smooth non-power-of-two lines: register-resident mixed-radix kernel
+    static const bool use_regmix = env_int("RFB200_NO_REGMIX", 0) == 0;
+    if (use_regmix && !job.pre_tab && !job.post_tab) {
+        const bool load_lf = !dims.empty() && iabs64(dims[0].is) < iabs64(job.is);
+        const bool store_lf = !dims.empty() && iabs64(dims[0].os) < iabs64(job.os);
+        if (launch_regmix(job, dims, load_lf, store_lf, alignment_ok(job, dims), s)) return;
+    }
     if (job.pre_tab || job.post_tab) {
         // fused factors exist only in the power-of-two kernel: long (or strided long) lines split first
         uint64_t a, b;

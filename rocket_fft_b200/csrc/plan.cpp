@@ -103,6 +103,25 @@ std::vector<uint32_t> radix_schedule(uint64_t n, uint32_t rmax) {
     return sched;
 }
 
+std::vector<uint32_t> regmix_schedule(uint64_t n, uint32_t max_pow2) {
+    std::vector<uint32_t> sched;
+    auto f = prime_factors(n);
+    int e2 = 0, cnt[14] = {0};
+    for (auto p : f) {
+        if (p == 2) ++e2;
+        else if (p <= 13) ++cnt[p];
+        else return {};
+    }
+    const int lg = max_pow2 >= 16 ? 4 : 3;
+    int big = e2 / lg, rem = e2 % lg;
+    for (int i = 0; i < big; ++i) sched.push_back(1u << lg);
+    // remainder as ONE smaller radix (8, 4 or 2), keeping the descending order
+    if (rem) sched.push_back(1u << rem);
+    for (int p : {13, 11, 7, 5, 3})
+        for (int i = 0; i < cnt[p]; ++i) sched.push_back((uint32_t)p);
+    return sched;
+}
+
 // ---------------------------------------------------------------------------------------
 // exact trigonometry
 // ---------------------------------------------------------------------------------------
@@ -178,9 +197,10 @@ void fill(std::vector<T> &h, TableKind kind, uint64_t n, uint64_t param, size_t 
 // stored at [(q-1)*ido_p + i].  Pass structure as in P2<LOGN> (pow2_kernel.cuh): one radix
 // 2/4/8 pass first when log2 n is not a multiple of 4, then radix-16 passes.
 template <typename T>
-void fill_stockham(std::vector<T> &h, uint64_t n, bool tile) {
+void fill_stockham(std::vector<T> &h, uint64_t n, int which, uint64_t param) {
     std::vector<uint32_t> rad;
-    if (tile) rad = radix_schedule(n, 64);
+    if (which == 1) rad = radix_schedule(n, 64);
+    else if (which == 2) rad = regmix_schedule(n, (uint32_t)param);
     else {
         int logn = 0;
         while ((1ull << logn) < n) ++logn;
@@ -225,19 +245,20 @@ const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool
         case TAB_CHIRP_FFT: count = param; break;
         case TAB_QUARTER: count = n + 1; break;
         case TAB_STOCKHAM:
+        case TAB_REGMIX:
         case TAB_TILE: count = n; break;  // upper bound: sum (R-1)*ido < n
     }
     size_t esz = prec ? 16 : 8;
     void *d = nullptr;
     RFB_CUDA_CHECK(cudaMalloc(&d, count * esz > 0 ? count * esz : esz));
-    if (kind == TAB_STOCKHAM || kind == TAB_TILE) {
+    if (kind == TAB_STOCKHAM || kind == TAB_TILE || kind == TAB_REGMIX) {
         if (prec) {
             std::vector<double> h;
-            fill_stockham(h, n, kind == TAB_TILE);
+            fill_stockham(h, n, kind == TAB_TILE ? 1 : (kind == TAB_REGMIX ? 2 : 0), param);
             RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
         } else {
             std::vector<float> h;
-            fill_stockham(h, n, kind == TAB_TILE);
+            fill_stockham(h, n, kind == TAB_TILE ? 1 : (kind == TAB_REGMIX ? 2 : 0), param);
             RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
     } else if (kind != TAB_CHIRP_FFT) {

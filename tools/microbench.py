@@ -118,7 +118,24 @@ def sizes():
             del x, y
 
 
-ALL = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "sizes": sizes}
+def nonpow2():
+    for n in (96, 100, 243, 360, 1000, 1080, 1536, 1920, 3000, 4000, 5000, 6561, 10000, 12288):
+        rows = max(4, (1 << 26) // (n * 8))
+        x = torch.randn(rows, n, dtype=torch.complex64, device=dev)
+        y = torch.empty_like(x)
+        run(f"c2c complex64 ({rows},{n})", lambda: R.c2c(x, y, [1], True, 1.0), 2 * x.numel() * 8, None, 10)
+        ms = timeit(lambda: torch.fft.fft(x, dim=1), 10)
+        report(f"   cuFFT [side ref]", ms, 2 * x.numel() * 8)
+        del x, y
+    x = torch.randn(64, 1080, 1920, dtype=torch.float32, device=dev)
+    X = torch.empty(64, 1080, 961, dtype=torch.complex64, device=dev)
+    nb = x.numel() * 4 + X.numel() * 8
+    run("rfft2 f32 64 x (1080,1920)", lambda: R.r2c(x, X, [1, 2], True, 1.0), nb, None, 5)
+    ms = timeit(lambda: torch.fft.rfft2(x), 5)
+    report("   cuFFT rfft2 [side ref]", ms, nb)
+
+
+ALL = {"nonpow2": nonpow2, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "sizes": sizes}
 if __name__ == "__main__":
     names = [a for a in sys.argv[1:] if a in ALL] or ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"]
     print(R.version(), torch.cuda.get_device_name(0))

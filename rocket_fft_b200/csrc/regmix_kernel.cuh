@@ -15,8 +15,7 @@
 
 namespace rfb {
 
-// points per thread: 16 complex floats or 8 complex doubles (32 data registers either way)
-template <typename T> constexpr int rm_e() { return sizeof(T) == 4 ? 16 : 8; }
+// points per thread E: 16 (short lines, small CTAs) or 32 (long lines); doubles use half of that
 constexpr int RM_MAXP = 12;    // passes
 
 struct RmPlan {
@@ -35,11 +34,11 @@ struct RmCtx {
     uint32_t tid;
 };
 
-template <typename T, int R, bool ALIGNED>
+template <typename T, int R, bool ALIGNED, int E>
 __device__ __forceinline__ void rm_pass(const TileGeom<T> &g, const RmPlan &pl, const RmCtx<T> &c, uint32_t s,
                                      bool &need_sync) {
     using C = cx<T>;
-    constexpr int JMAX = rm_e<T>() / R;
+    constexpr int JMAX = E / R;
     C v[JMAX * R];
     const uint32_t n = g.n, nb = n / R, ido = pl.ido[s], J = pl.J[s], TPL = pl.TPL;
     const bool first = (s == 0), last = (s + 1 == pl.npass);
@@ -148,7 +147,7 @@ __device__ __forceinline__ void rm_pass(const TileGeom<T> &g, const RmPlan &pl, 
 // plan.cpp): one run-time loop per radix keeps every unrolled pass body -- and its register tile -- in a
 // straight-line region of the kernel (a switch inside a loop over passes made ptxas demote the tiles to
 // local memory).
-template <typename T, bool ALIGNED, int THREADS, int MINB>
+template <typename T, bool ALIGNED, int E, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) fft_regmix_kernel(const TileGeom<T> g, const RmPlan pl) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw_rm[];
@@ -166,12 +165,12 @@ __global__ void __launch_bounds__(THREADS, MINB) fft_regmix_kernel(const TileGeo
     uint32_t s = 0;
 #define RFB_RM_RUN(RR)                                           \
     while (s < pl.npass && pl.R[s] == RR) {                      \
-        rm_pass<T, RR, ALIGNED>(g, pl, c, s, need_sync);          \
+        rm_pass<T, RR, ALIGNED, E>(g, pl, c, s, need_sync);          \
         ++s;                                                     \
     }
-    if constexpr (rm_e<T>() >= 16) { RFB_RM_RUN(16) }
+    if constexpr (E >= 16) { RFB_RM_RUN(16) }
     RFB_RM_RUN(8) RFB_RM_RUN(4) RFB_RM_RUN(2)
-    if constexpr (rm_e<T>() >= 16) { RFB_RM_RUN(13) RFB_RM_RUN(11) }
+    if constexpr (E >= 16) { RFB_RM_RUN(13) RFB_RM_RUN(11) }
     RFB_RM_RUN(7) RFB_RM_RUN(5) RFB_RM_RUN(3)
 #undef RFB_RM_RUN
 }

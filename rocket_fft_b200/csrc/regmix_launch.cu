@@ -8,14 +8,14 @@ namespace rfb {
 
 static const size_t RM_MAX_SMEM = 227 * 1024;
 
-template <typename T, bool ALIGNED, int THREADS, int MINB>
+template <typename T, bool ALIGNED, int E, int THREADS, int MINB>
 static void launch_regmix_inst(const LineJob &job, const std::vector<Dim> &dims, const RmPlan &pl, uint32_t W,
                                bool load_lf, bool store_lf, cudaStream_t s) {
     TileGeom<T> g;
     const uint64_t ntiles = fill_geom<T>(g, job, dims, W, load_lf, store_lf);
-    g.ptw = (const cx<T> *)get_table(TAB_REGMIX, job.prec, job.n, rm_e<T>() >= 16 ? 16 : 8);
+    g.ptw = (const cx<T> *)get_table(TAB_REGMIX, job.prec, job.n, sizeof(T) == 4 ? 16 : 8);  // = maxp2 of the schedule
     const size_t smem = (size_t)W * pl.pitch * sizeof(cx<T>);
-    auto kern = fft_regmix_kernel<T, ALIGNED, THREADS, MINB>;
+    auto kern = fft_regmix_kernel<T, ALIGNED, E, THREADS, MINB>;
     static thread_local int dev_set = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -30,10 +30,17 @@ static void launch_regmix_inst(const LineJob &job, const std::vector<Dim> &dims,
 
 template <typename T, bool ALIGNED>
 static void launch_regmix_typed(const LineJob &job, const std::vector<Dim> &dims, const RmPlan &pl, uint32_t W,
-                                bool load_lf, bool store_lf, cudaStream_t s) {
-    // small CTAs (<= 256 threads, 3 per SM) for short lines, one 512-thread CTA per SM for long ones
-    if (W * pl.TPL <= 256) launch_regmix_inst<T, ALIGNED, 256, 3>(job, dims, pl, W, load_lf, store_lf, s);
-    else launch_regmix_inst<T, ALIGNED, 512, 1>(job, dims, pl, W, load_lf, store_lf, s);
+                                uint32_t E, bool load_lf, bool store_lf, cudaStream_t s) {
+    constexpr int E1 = sizeof(T) == 4 ? 16 : 8, E2 = 2 * E1;
+    // small register tiles and CTAs (<= 256 threads, 3 per SM) for short lines, double tiles for long ones
+    const bool small_cta = W * pl.TPL <= 256;
+    if (E == (uint32_t)E1) {
+        if (small_cta) launch_regmix_inst<T, ALIGNED, E1, 256, 3>(job, dims, pl, W, load_lf, store_lf, s);
+        else launch_regmix_inst<T, ALIGNED, E1, 512, 1>(job, dims, pl, W, load_lf, store_lf, s);
+    } else {
+        if (small_cta) launch_regmix_inst<T, ALIGNED, E2, 256, 2>(job, dims, pl, W, load_lf, store_lf, s);
+        else launch_regmix_inst<T, ALIGNED, E2, 512, 1>(job, dims, pl, W, load_lf, store_lf, s);
+    }
 }
 
 bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
@@ -43,19 +50,31 @@ bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_l
     if (n < 6 || n > 16384) return false;
     if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
     if (!job.split_out.empty() || job.pre_tab || job.post_tab) return false;
-    // the very schedule the pass-major twiddle table (TAB_REGMIX) is built for
-    const uint32_t E = job.prec ? 8 : 16;
-    std::vector<uint32_t> sched = regmix_schedule(n, E);
+    // the very schedule the pass-major twiddle table (TAB_REGMIX) is built for; points per thread E:
+    // the small tile if the line then needs at most 256 threads, else the double tile
+    const uint32_t E1 = job.prec ? 8 : 16;
+    const uint32_t maxp2 = job.prec ? 8 : 16;  // largest power-of-two radix (table key); double tiles keep it
+    std::vector<uint32_t> sched = regmix_schedule(n, maxp2);
     if (sched.empty() || sched.size() > (size_t)RM_MAXP) return false;
-    for (auto R : sched)
-        if (R > E) return false;
     RmPlan pl;
     memset(&pl, 0, sizeof(pl));
     pl.npass = (uint32_t)sched.size();
-    uint32_t TPL = 1;
-    for (auto R : sched) {
-        const uint32_t nb = (uint32_t)(n / R), jmax = E / R;
-        TPL = std::max(TPL, (nb + jmax - 1) / jmax);
+    auto tpl_for = [&](uint32_t e, bool &ok) {
+        ok = true;
+        uint32_t tpl = 1;
+        for (auto R : sched) {
+            if (R > e) { ok = false; return 0u; }
+            const uint32_t nb = (uint32_t)(n / R), jmax = e / R;
+            tpl = std::max(tpl, (nb + jmax - 1) / jmax);
+        }
+        return tpl;
+    };
+    bool ok1 = false, ok2 = false;
+    uint32_t E = E1, TPL = tpl_for(E1, ok1);
+    if (!ok1 || TPL > 256) {
+        E = 2 * E1;
+        TPL = tpl_for(E, ok2);
+        if (!ok2) return false;
     }
     const size_t esz = job.prec ? 16 : 8;
     const bool lf = load_lf || store_lf;
@@ -87,11 +106,11 @@ bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_l
     pl.pitch = (uint32_t)n | 1u;
     if ((size_t)W * pl.pitch * esz > RM_MAX_SMEM) return false;
     if (job.prec) {
-        if (aligned) launch_regmix_typed<double, true>(job, dims, pl, W, load_lf, store_lf, s);
-        else launch_regmix_typed<double, false>(job, dims, pl, W, load_lf, store_lf, s);
+        if (aligned) launch_regmix_typed<double, true>(job, dims, pl, W, E, load_lf, store_lf, s);
+        else launch_regmix_typed<double, false>(job, dims, pl, W, E, load_lf, store_lf, s);
     } else {
-        if (aligned) launch_regmix_typed<float, true>(job, dims, pl, W, load_lf, store_lf, s);
-        else launch_regmix_typed<float, false>(job, dims, pl, W, load_lf, store_lf, s);
+        if (aligned) launch_regmix_typed<float, true>(job, dims, pl, W, E, load_lf, store_lf, s);
+        else launch_regmix_typed<float, false>(job, dims, pl, W, E, load_lf, store_lf, s);
     }
     return true;
 }

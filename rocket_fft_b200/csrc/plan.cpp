@@ -103,22 +103,39 @@ std::vector<uint32_t> radix_schedule(uint64_t n, uint32_t rmax) {
     return sched;
 }
 
-std::vector<uint32_t> regmix_schedule(uint64_t n, uint32_t max_pow2) {
-    std::vector<uint32_t> sched;
-    auto f = prime_factors(n);
-    int e2 = 0, cnt[14] = {0};
-    for (auto p : f) {
-        if (p == 2) ++e2;
-        else if (p <= 13) ++cnt[p];
-        else return {};
+namespace {
+// fewest radices (all <= cap, from the kernel's set) whose product is n; non-increasing search
+void regmix_search(uint64_t n, uint32_t maxr, const uint32_t *rad, int nrad, std::vector<uint32_t> &cur,
+                   std::vector<uint32_t> &best) {
+    if (n == 1) {
+        if (best.empty() || cur.size() < best.size()) best = cur;
+        return;
     }
-    const int lg = max_pow2 >= 16 ? 4 : 3;
-    int big = e2 / lg, rem = e2 % lg;
-    for (int i = 0; i < big; ++i) sched.push_back(1u << lg);
-    // remainder as ONE smaller radix (8, 4 or 2), keeping the descending order
-    if (rem) sched.push_back(1u << rem);
-    for (int p : {13, 11, 7, 5, 3})
-        for (int i = 0; i < cnt[p]; ++i) sched.push_back((uint32_t)p);
+    if (!best.empty() && cur.size() + 1 >= best.size()) return;
+    for (int i = 0; i < nrad; ++i) {
+        const uint32_t R = rad[i];
+        if (R > maxr || n % R) continue;
+        cur.push_back(R);
+        regmix_search(n / R, R, rad, nrad, cur, best);
+        cur.pop_back();
+    }
+}
+}  // namespace
+
+std::vector<uint32_t> regmix_schedule(uint64_t n, uint32_t cap) {
+    static const uint32_t all[14] = {16, 15, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    for (auto p : prime_factors(n))
+        if (p > 13 || p > cap) return {};
+    std::vector<uint32_t> cur, best;
+    regmix_search(n, cap, all, 14, cur, best);
+    if (best.empty()) return {};
+    // the kernel runs the radices in this fixed order (powers of two first: their reads have the
+    // longest unit-stride runs; odd radices last: conflict-free at small inner strides)
+    static const uint32_t order[14] = {16, 8, 4, 2, 12, 10, 6, 15, 13, 11, 9, 7, 5, 3};
+    std::vector<uint32_t> sched;
+    for (auto R : order)
+        for (auto r : best)
+            if (r == R) sched.push_back(R);
     return sched;
 }
 

@@ -19,9 +19,10 @@ uint64_t largest_prime_factor(uint64_t n);
 // Radix schedule for an in-shared-memory line transform: products of 2s grouped into
 // 16/8/4/2, then odd primes ascending.  Empty if some prime factor exceeds `rmax`.
 std::vector<uint32_t> radix_schedule(uint64_t n, uint32_t rmax);
-// Schedule of the register-resident mixed-radix kernel: radices grouped in the order
-// 16, 8, 4, 2, 13, 11, 7, 5, 3 (powers of two capped at max_pow2).  Empty if n has a prime factor > 13.
-std::vector<uint32_t> regmix_schedule(uint64_t n, uint32_t max_pow2);
+// Schedule of the register-resident mixed-radix kernel: the fewest radices from
+// {16,15,13,12,11,10,9,8,7,6,5,4,3,2} (each <= cap) with product n, in the kernel's fixed order
+// 16,8,4,2,12,10,6,15,13,11,9,7,5,3.  Empty if n has a prime factor > min(13, cap).
+std::vector<uint32_t> regmix_schedule(uint64_t n, uint32_t cap);
 
 // cos/sin of 2*pi*num/den with octant reduction in long double.
 void sincos_2pi(uint64_t num, uint64_t den, long double &c, long double &s);
@@ -33,7 +34,7 @@ enum TableKind : int {
     TAB_CHIRP = 3,     // exp(-i pi t^2 / n), t in [0, n)
     TAB_CHIRP_FFT = 4, // forward DFT_M of the wrapped conjugate chirp, divided by M  (param = M)
     TAB_QUARTER = 5,   // exp(-2 pi i t / (4 n)), t in [0, n]   (DCT/DST and real pre/post factors)
-    TAB_REGMIX = 8,    // pass-major twiddles for regmix_schedule(n, param)  (param = largest power-of-two radix)
+    TAB_REGMIX = 8,    // pass-major twiddles for regmix_schedule(n, param)  (param = radix cap)
     TAB_TILE = 7,      // pass-major twiddles of the generic tile kernel for radix_schedule(n, 64)
     TAB_STOCKHAM = 6,  // per-pass twiddles of the power-of-two register kernel (n = 2^k), see pow2_kernel.cuh
 };

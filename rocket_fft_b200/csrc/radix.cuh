@@ -184,4 +184,96 @@ template <typename T> struct Dft<T, 7> : DftPrime<T, 7> {};
 template <typename T> struct Dft<T, 11> : DftPrime<T, 11> {};
 template <typename T> struct Dft<T, 13> : DftPrime<T, 13> {};
 
+// cos / sin of 2 pi j / R for the composite radices (correctly rounded doubles)
+template <int R> struct RootTab;
+template <> struct RootTab<6> {
+    __host__ __device__ static constexpr double c(int j) {
+        constexpr double t[6] = {1.0, 0.5, -0.5, -1.0, -0.5, 0.5};
+        return t[j];
+    }
+    __host__ __device__ static constexpr double s(int j) {
+        constexpr double t[6] = {0.0, 0.8660254037844386, 0.8660254037844386, 0.0, -0.8660254037844386, -0.8660254037844386};
+        return t[j];
+    }
+};
+template <> struct RootTab<9> {
+    __host__ __device__ static constexpr double c(int j) {
+        constexpr double t[9] = {1.0, 0.766044443118978, 0.17364817766693036, -0.5, -0.9396926207859084, -0.9396926207859084, -0.5, 0.17364817766693036, 0.766044443118978};
+        return t[j];
+    }
+    __host__ __device__ static constexpr double s(int j) {
+        constexpr double t[9] = {0.0, 0.6427876096865394, 0.984807753012208, 0.8660254037844386, 0.3420201433256687, -0.3420201433256687, -0.8660254037844386, -0.984807753012208, -0.6427876096865394};
+        return t[j];
+    }
+};
+template <> struct RootTab<10> {
+    __host__ __device__ static constexpr double c(int j) {
+        constexpr double t[10] = {1.0, 0.8090169943749475, 0.30901699437494745, -0.30901699437494745, -0.8090169943749475, -1.0, -0.8090169943749475, -0.30901699437494745, 0.30901699437494745, 0.8090169943749475};
+        return t[j];
+    }
+    __host__ __device__ static constexpr double s(int j) {
+        constexpr double t[10] = {0.0, 0.5877852522924731, 0.9510565162951535, 0.9510565162951535, 0.5877852522924731, 0.0, -0.5877852522924731, -0.9510565162951535, -0.9510565162951535, -0.5877852522924731};
+        return t[j];
+    }
+};
+template <> struct RootTab<12> {
+    __host__ __device__ static constexpr double c(int j) {
+        constexpr double t[12] = {1.0, 0.8660254037844386, 0.5, 0.0, -0.5, -0.8660254037844386, -1.0, -0.8660254037844386, -0.5, 0.0, 0.5, 0.8660254037844386};
+        return t[j];
+    }
+    __host__ __device__ static constexpr double s(int j) {
+        constexpr double t[12] = {0.0, 0.5, 0.8660254037844386, 1.0, 0.8660254037844386, 0.5, 0.0, -0.5, -0.8660254037844386, -1.0, -0.8660254037844386, -0.5};
+        return t[j];
+    }
+};
+template <> struct RootTab<15> {
+    __host__ __device__ static constexpr double c(int j) {
+        constexpr double t[15] = {1.0, 0.9135454576426009, 0.6691306063588582, 0.30901699437494745, -0.10452846326765347, -0.5, -0.8090169943749475, -0.9781476007338057, -0.9781476007338057, -0.8090169943749475, -0.5, -0.10452846326765347, 0.30901699437494745, 0.6691306063588582, 0.9135454576426009};
+        return t[j];
+    }
+    __host__ __device__ static constexpr double s(int j) {
+        constexpr double t[15] = {0.0, 0.4067366430758002, 0.7431448254773942, 0.9510565162951535, 0.9945218953682733, 0.8660254037844386, 0.5877852522924731, 0.20791169081775934, -0.20791169081775934, -0.5877852522924731, -0.8660254037844386, -0.9945218953682733, -0.9510565162951535, -0.7431448254773942, -0.4067366430758002};
+        return t[j];
+    }
+};
+
+// Composite radix R = P*Q in registers (Cooley-Tukey): Q transforms of size P over x[Q p + q], the
+// internal factors exp(-2 pi i q k1 / R), then P transforms of size Q; X[k1 + P k2].
+template <typename T, int P, int Q> struct DftComposite {
+    using C = cx<T>;
+    static __device__ __forceinline__ void run(C *v) {
+        constexpr int R = P * Q;
+        C a[Q][P];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) a[q][p] = v[Q * p + q];
+            Dft<T, P>::run(a[q]);
+        }
+#pragma unroll
+        for (int q = 1; q < Q; ++q)
+#pragma unroll
+            for (int k1 = 1; k1 < P; ++k1) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int j = (q * k1) % R;
+                a[q][k1] = cmul(a[q][k1], mk<T>(T(RootTab<R>::c(j)), T(-RootTab<R>::s(j))));
+            }
+#pragma unroll
+        for (int k1 = 0; k1 < P; ++k1) {
+            C b[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) b[q] = a[q][k1];
+            Dft<T, Q>::run(b);
+#pragma unroll
+            for (int k2 = 0; k2 < Q; ++k2) v[k1 + P * k2] = b[k2];
+        }
+    }
+};
+template <typename T> struct Dft<T, 6> : DftComposite<T, 3, 2> {};
+template <typename T> struct Dft<T, 9> : DftComposite<T, 3, 3> {};
+template <typename T> struct Dft<T, 10> : DftComposite<T, 5, 2> {};
+template <typename T> struct Dft<T, 12> : DftComposite<T, 4, 3> {};
+template <typename T> struct Dft<T, 15> : DftComposite<T, 5, 3> {};
+
 }  // namespace rfb

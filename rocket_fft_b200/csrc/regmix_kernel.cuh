@@ -3,7 +3,7 @@
 // Same idea as pow2_kernel.cuh -- the first pass reads global memory straight into registers, the
 // last pass writes registers straight to global memory (both coalesced: thread t touches t + m*n/R),
 // and between passes the line makes one trip through shared memory -- but the radix of every pass is
-// a run-time choice from {2,3,4,5,7,8,11,13,16}.  A thread owns up to 16 points: J = ceil((n/R)/TPL)
+// a run-time choice from {2,...,13,15,16} (6, 9, 10, 12, 15 as nested butterflies).  A thread owns up to 16 points: J = ceil((n/R)/TPL)
 // butterflies of radix R per pass (J*R <= 16), butterfly b = t + j*TPL.  TPL (threads per line) is
 // chosen by the host so that every pass fits.  Covers the lengths the reference's cfftp handles
 // with pass2/3/4/5/7/8/11 (rocket_fft/_pocketfft_hdronly.h:1079-1573) plus 13 and 16.
@@ -19,7 +19,7 @@ namespace rfb {
 constexpr int RM_MAXP = 12;    // passes
 
 struct RmPlan {
-    uint32_t npass, TPL;
+    uint32_t npass, TPL, cap;
     FastDiv d_TPL;
     uint32_t R[RM_MAXP], ido[RM_MAXP], J[RM_MAXP], twoff[RM_MAXP];
     FastDiv d_ido[RM_MAXP];
@@ -143,7 +143,7 @@ __device__ __forceinline__ void rm_pass(const TileGeom<T> &g, const RmPlan &pl, 
     }
 }
 
-// Passes are grouped by radix in the fixed order 16, 8, 4, 2, 13, 11, 7, 5, 3 (regmix_schedule in
+// Passes are grouped by radix in the fixed order 16,8,4,2,12,10,6,15,13,11,9,7,5,3 (regmix_schedule in
 // plan.cpp): one run-time loop per radix keeps every unrolled pass body -- and its register tile -- in a
 // straight-line region of the kernel (a switch inside a loop over passes made ptxas demote the tiles to
 // local memory).
@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fft_regmix_kernel(const TileGeo
     }
     if constexpr (E >= 16) { RFB_RM_RUN(16) }
     RFB_RM_RUN(8) RFB_RM_RUN(4) RFB_RM_RUN(2)
-    if constexpr (E >= 16) { RFB_RM_RUN(13) RFB_RM_RUN(11) }
+    if constexpr (E >= 16) { RFB_RM_RUN(12) RFB_RM_RUN(10) }
+    RFB_RM_RUN(6)
+    if constexpr (E >= 16) { RFB_RM_RUN(15) RFB_RM_RUN(13) RFB_RM_RUN(11) RFB_RM_RUN(9) }
     RFB_RM_RUN(7) RFB_RM_RUN(5) RFB_RM_RUN(3)
 #undef RFB_RM_RUN
 }

@@ -13,7 +13,7 @@ static void launch_regmix_inst(const LineJob &job, const std::vector<Dim> &dims,
                                bool load_lf, bool store_lf, cudaStream_t s) {
     TileGeom<T> g;
     const uint64_t ntiles = fill_geom<T>(g, job, dims, W, load_lf, store_lf);
-    g.ptw = (const cx<T> *)get_table(TAB_REGMIX, job.prec, job.n, sizeof(T) == 4 ? 16 : 8);  // = maxp2 of the schedule
+    g.ptw = (const cx<T> *)get_table(TAB_REGMIX, job.prec, job.n, pl.cap);
     const size_t smem = (size_t)W * pl.pitch * sizeof(cx<T>);
     auto kern = fft_regmix_kernel<T, ALIGNED, E, THREADS, MINB>;
     static thread_local int dev_set = -1;
@@ -43,9 +43,17 @@ static void launch_regmix_typed(const LineJob &job, const std::vector<Dim> &dims
     }
 }
 
+#ifdef RFB_RM_DOUBLE
+bool launch_regmix_f64(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
+                       cudaStream_t s) {
+#else
+bool launch_regmix_f64(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
+                       cudaStream_t s);
 bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
                    cudaStream_t s) {
-    if (dims.size() > (size_t)MAXB) return false;
+    if (job.prec) return launch_regmix_f64(job, dims, load_lf, store_lf, aligned, s);
+#endif
+    if (dims.size() > (size_t)MAXB || !aligned) return false;
     const uint64_t n = job.n;
     if (n < 6 || n > 16384) return false;
     if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
@@ -53,12 +61,17 @@ bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_l
     // the very schedule the pass-major twiddle table (TAB_REGMIX) is built for; points per thread E:
     // the small tile if the line then needs at most 256 threads, else the double tile
     const uint32_t E1 = job.prec ? 8 : 16;
-    const uint32_t maxp2 = job.prec ? 8 : 16;  // largest power-of-two radix (table key); double tiles keep it
-    std::vector<uint32_t> sched = regmix_schedule(n, maxp2);
+    uint32_t cap = E1;  // radix cap = table key
+    std::vector<uint32_t> sched = regmix_schedule(n, cap);
+    if (sched.empty() && job.prec) {  // doubles with a factor 11 or 13: only the 16-point tile takes them
+        cap = 16;
+        sched = regmix_schedule(n, cap);
+    }
     if (sched.empty() || sched.size() > (size_t)RM_MAXP) return false;
     RmPlan pl;
     memset(&pl, 0, sizeof(pl));
     pl.npass = (uint32_t)sched.size();
+    pl.cap = cap;
     auto tpl_for = [&](uint32_t e, bool &ok) {
         ok = true;
         uint32_t tpl = 1;
@@ -71,7 +84,7 @@ bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_l
     };
     bool ok1 = false, ok2 = false;
     uint32_t E = E1, TPL = tpl_for(E1, ok1);
-    if (!ok1 || TPL > 256) {
+    if (!ok1 || TPL > 512) {  // (measured: the small tile with one 512-thread CTA beats the double tile)
         E = 2 * E1;
         TPL = tpl_for(E, ok2);
         if (!ok2) return false;
@@ -105,13 +118,12 @@ bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_l
     }
     pl.pitch = (uint32_t)n | 1u;
     if ((size_t)W * pl.pitch * esz > RM_MAX_SMEM) return false;
-    if (job.prec) {
-        if (aligned) launch_regmix_typed<double, true>(job, dims, pl, W, E, load_lf, store_lf, s);
-        else launch_regmix_typed<double, false>(job, dims, pl, W, E, load_lf, store_lf, s);
-    } else {
-        if (aligned) launch_regmix_typed<float, true>(job, dims, pl, W, E, load_lf, store_lf, s);
-        else launch_regmix_typed<float, false>(job, dims, pl, W, E, load_lf, store_lf, s);
-    }
+    // (unaligned complex arrays stay on the generic tile kernel: halves the build time of this file)
+#ifdef RFB_RM_DOUBLE
+    launch_regmix_typed<double, true>(job, dims, pl, W, E, load_lf, store_lf, s);
+#else
+    launch_regmix_typed<float, true>(job, dims, pl, W, E, load_lf, store_lf, s);
+#endif
     return true;
 }
 

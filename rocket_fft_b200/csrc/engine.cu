@@ -47,6 +47,8 @@ static void init_pool_once() {
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(mu);
     if (dev < 64 && !done[dev]) {
+        const int l2g = env_int("RFB200_L2_FETCH", 0);
+        if (l2g > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2g);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t thr = UINT64_MAX;
@@ -382,6 +384,7 @@ static bool normalise(LineJob &job, std::vector<Dim> &dims) {
 }
 
 void run_lines(const LineJob &job_in, cudaStream_t s) {
+    init_pool_once();
     LineJob job = job_in;
     std::vector<Dim> dims;
     if (!normalise(job, dims)) return;

@@ -95,6 +95,7 @@ bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_l
     if (lf) {
         W = (uint32_t)(128 / esz);  // 128-byte rows of neighbouring lines
         if (W * TPL > 512) W = (uint32_t)(64 / esz);
+        if (W * TPL > 512) W = (uint32_t)(32 / esz);  // one 32-byte sector per row: still beats the generic kernel
         if (W * TPL > 512) return false;
     } else {
         W = std::max<uint32_t>(1, 256 / TPL);

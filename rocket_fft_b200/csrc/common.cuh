@@ -1,7 +1,18 @@
 // Shared device/host helpers for the rocketfft_b200 kernels (sm_100a).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+// NVRTC (run-time specialisation, jit.cu): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned long size_t;
+typedef unsigned long uintptr_t;
+#endif
 
 namespace rfb {
 
@@ -57,7 +68,7 @@ template <typename C, typename T> __device__ __forceinline__ C cscale(C a, T s) 
 struct FastDiv {
     uint32_t d, mul, sh;
 };
-inline FastDiv make_fastdiv(uint32_t d) {
+__host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
     FastDiv f;
     f.d = d;
     uint32_t sh = 0;

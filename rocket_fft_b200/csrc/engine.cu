@@ -442,7 +442,9 @@ static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStrea
     if (use_regmix && !job.pre_tab && !job.post_tab) {
         const bool load_lf = !dims.empty() && iabs64(dims[0].is) < iabs64(job.is);
         const bool store_lf = !dims.empty() && iabs64(dims[0].os) < iabs64(job.os);
-        if (launch_regmix(job, dims, load_lf, store_lf, alignment_ok(job, dims), s)) return;
+        const bool al = alignment_ok(job, dims);
+        if (launch_spec_jit(job, dims, load_lf, store_lf, al, s)) return;
+        if (launch_regmix(job, dims, load_lf, store_lf, al, s)) return;
     }
     if (job.pre_tab || job.post_tab) {
         // fused factors exist only in the power-of-two kernel: long (or strided long) lines split first

@@ -80,6 +80,9 @@ inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<
 // pow2_launch_*.cu: returns false when the job is not one the register kernel takes
 bool launch_pow2_f32(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s);
 bool launch_pow2_f64(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s);
+// jit.cu: run-time specialised kernel for smooth non-power-of-two lengths (NVRTC); false if not taken
+bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
+                     cudaStream_t s);
 // regmix_launch.cu: smooth lengths (prime factors <= 13) that fit a register tile
 bool launch_regmix(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
                    cudaStream_t s);

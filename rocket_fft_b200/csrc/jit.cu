@@ -1,0 +1,261 @@
+// Run-time specialisation of the register-resident Stockham kernel (spec_kernel.cuh) for the length at hand.
+//
+// For smooth non-power-of-two lengths the generic run-time-radix kernel (regmix_kernel.cuh) spends about
+// half of its issue slots on index arithmetic and guards that are compile-time constants once n is known
+// (measured: n = 1000: 27.8 % -> 54.2 % of HBM peak with the specialised instantiation).  The set of lengths is
+// open-ended, so the instantiation happens on first use: NVRTC compiles `fft_spec_kernel<T, Plan, true>` from
+// the same headers the build uses (-I csrc), for sm_100a, and the cubin is loaded with cudaLibraryLoadData.
+// Plans are cached per (device, precision, n, threads-per-line, lines-per-CTA).  If NVRTC cannot be loaded or a
+// compilation fails the caller silently stays on the build-time kernels (regmix / tile) -- still CUDA, never CPU.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "geom_fill.cuh"
+
+namespace rfb {
+
+namespace {
+
+// ---- minimal NVRTC binding through dlopen ---------------------------------------------------------------
+typedef struct _nvrtcProgram *nvrtcProgram;
+struct Nvrtc {
+    void *h = nullptr;
+    int (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+    int (*DestroyProgram)(nvrtcProgram *);
+    int (*CompileProgram)(nvrtcProgram, int, const char *const *);
+    int (*GetProgramLogSize)(nvrtcProgram, size_t *);
+    int (*GetProgramLog)(nvrtcProgram, char *);
+    int (*AddNameExpression)(nvrtcProgram, const char *);
+    int (*GetLoweredName)(nvrtcProgram, const char *, const char **);
+    int (*GetCUBINSize)(nvrtcProgram, size_t *);
+    int (*GetCUBIN)(nvrtcProgram, char *);
+    bool ok = false;
+};
+
+Nvrtc &nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *cands[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                               "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (auto c : cands) {
+            n.h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+            if (n.h) break;
+        }
+        if (!n.h) return;
+#define RFB_SYM(field, name)                          \
+    *(void **)(&n.field) = dlsym(n.h, name);          \
+    if (!n.field) return;
+        RFB_SYM(CreateProgram, "nvrtcCreateProgram")
+        RFB_SYM(DestroyProgram, "nvrtcDestroyProgram")
+        RFB_SYM(CompileProgram, "nvrtcCompileProgram")
+        RFB_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+        RFB_SYM(GetProgramLog, "nvrtcGetProgramLog")
+        RFB_SYM(AddNameExpression, "nvrtcAddNameExpression")
+        RFB_SYM(GetLoweredName, "nvrtcGetLoweredName")
+        RFB_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+        RFB_SYM(GetCUBIN, "nvrtcGetCUBIN")
+#undef RFB_SYM
+        n.ok = true;
+    });
+    return n;
+}
+
+// directory of the kernel headers: <dir of this shared object>/csrc
+std::string header_dir() {
+    Dl_info info;
+    if (dladdr((void *)&header_dir, &info) && info.dli_fname) {
+        std::string p(info.dli_fname);
+        size_t k = p.rfind('/');
+        return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/csrc";
+    }
+    return "csrc";
+}
+
+struct SpecKey {
+    int dev, prec;
+    uint64_t n;
+    uint32_t tpl, w;
+    bool operator<(const SpecKey &o) const {
+        return std::tie(dev, prec, n, tpl, w) < std::tie(o.dev, o.prec, o.n, o.tpl, o.w);
+    }
+};
+struct SpecEntry {
+    cudaKernel_t kern = nullptr;  // nullptr: compilation failed, do not retry
+    size_t smem = 0;
+    uint32_t cap = 16;
+};
+std::mutex g_mu;
+std::map<SpecKey, SpecEntry> g_cache;
+
+bool compile_spec(int prec, uint64_t n, uint32_t tpl, uint32_t w, uint32_t minb, const std::vector<uint32_t> &sched,
+                  SpecEntry &out) {
+    Nvrtc &rt = nvrtc();
+    if (!rt.ok) return false;
+    const char *T = prec ? "double" : "float";
+    std::string rad;
+    for (size_t i = 0; i < sched.size(); ++i) rad += (i ? ", " : "") + std::to_string(sched[i]);
+    char src[2048];
+    snprintf(src, sizeof(src),
+             "#include \"spec_kernel.cuh\"\n"
+             "namespace rfb {\n"
+             "struct PJ {\n"
+             "    static constexpr int N = %llu, TPL = %u, W = %u, NPASS = %zu, MINB = %u;\n"
+             "    __host__ __device__ static constexpr int radix(int s) { constexpr int r[%zu] = {%s}; return r[s]; }\n"
+             "};\n"
+             "template __global__ void fft_spec_kernel<%s, PJ, true>(const TileGeom<%s>);\n"
+             "}\n",
+             (unsigned long long)n, tpl, w, sched.size(), minb, sched.size(), rad.c_str(), T, T);
+    nvrtcProgram prog = nullptr;
+    if (rt.CreateProgram(&prog, src, "rfb_spec.cu", 0, nullptr, nullptr) != 0) return false;
+    const std::string name = std::string("rfb::fft_spec_kernel<") + T + ", rfb::PJ, true>";
+    rt.AddNameExpression(prog, name.c_str());
+    const std::string inc = "-I" + header_dir();
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", inc.c_str(), "-default-device", "-lineinfo"};
+    const int rc = rt.CompileProgram(prog, 5, opts);
+    if (rc != 0) {
+        if (getenv("RFB200_JIT_VERBOSE")) {
+            size_t ls = 0;
+            rt.GetProgramLogSize(prog, &ls);
+            std::string log(ls + 1, '\0');
+            rt.GetProgramLog(prog, &log[0]);
+            fprintf(stderr, "rocketfft_b200: NVRTC failed for n=%llu:\n%s\n", (unsigned long long)n, log.c_str());
+        }
+        rt.DestroyProgram(&prog);
+        return false;
+    }
+    const char *lowered = nullptr;
+    size_t cs = 0;
+    bool ok = rt.GetLoweredName(prog, name.c_str(), &lowered) == 0 && lowered && rt.GetCUBINSize(prog, &cs) == 0 && cs > 0;
+    std::vector<char> cubin(cs);
+    ok = ok && rt.GetCUBIN(prog, cubin.data()) == 0;
+    std::string lname = lowered ? lowered : "";
+    rt.DestroyProgram(&prog);
+    if (!ok) return false;
+    cudaLibrary_t lib = nullptr;
+    if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaKernel_t k = nullptr;
+    if (cudaLibraryGetKernel(&k, lib, lname.c_str()) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    out.kern = k;
+    return true;
+}
+
+}  // namespace
+
+// Returns true if the job was launched on a run-time specialised kernel.
+bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
+                     cudaStream_t s) {
+    static const int mode = [] {
+        const char *v = getenv("RFB200_JIT");
+        return v ? atoi(v) : 1;  // 0: off, 1: for large batches, 2: always
+    }();
+    if (mode == 0 || !aligned || dims.size() > (size_t)MAXB) return false;
+    const uint64_t n = job.n;
+    if (n < 6 || n > 32768 || (n & (n - 1)) == 0) return false;
+    if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
+    if (!job.split_out.empty() || job.pre_tab || job.post_tab) return false;
+    uint64_t lines = 1;
+    for (auto &d : dims) lines *= (uint64_t)d.n;
+    // a compilation costs ~1 s: only for work that repays it (or when forced)
+    if (mode == 1 && lines * n < (1ull << 21)) return false;
+    const size_t esz = job.prec ? 16 : 8;
+    uint32_t cap = job.prec ? 8 : 16;
+    std::vector<uint32_t> sched = regmix_schedule(n, cap);
+    if (sched.empty() && job.prec) {
+        cap = 16;
+        sched = regmix_schedule(n, cap);
+    }
+    if (sched.empty() || sched.size() > 12) return false;
+    // points per thread: small budget first (more threads, fewer registers), the double budget for long lines
+    const uint32_t e1 = job.prec ? 8 : 16;
+    const bool lf = load_lf || store_lf;
+    uint32_t tpl = 0, eb = 0;
+    for (uint32_t e : {e1, 2 * e1}) {
+        bool ok = true;
+        uint32_t t = 1;
+        for (auto R : sched) {
+            if (R > e) { ok = false; break; }
+            const uint32_t nb = (uint32_t)(n / R), jmax = e / R;
+            t = std::max(t, (nb + jmax - 1) / jmax);
+        }
+        const uint32_t tmax = (e == e1) ? 1024u : 512u;
+        if (ok && t <= (lf ? tmax / 4 : tmax)) { tpl = t; eb = e; break; }
+    }
+    if (!tpl) return false;
+    const uint32_t tmax = (eb == e1) ? 1024u : 512u;
+    uint32_t w;
+    if (lf) {
+        w = (uint32_t)(128 / esz);
+        while (w > 1 && w * tpl > tmax) w /= 2;
+        if (w * esz < 32) return false;
+    } else {
+        w = std::max<uint32_t>(1, 256 / tpl);
+        const uint64_t e0 = dims.empty() ? 1 : (uint64_t)dims[0].n;
+        w = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(w, e0));
+    }
+    const uint32_t threads = w * tpl;
+    if (threads > tmax) return false;
+    const uint32_t pitch = (w == 1) ? (uint32_t)n : ((uint32_t)n | 1u);
+    const size_t smem = (size_t)w * pitch * esz;
+    if (smem > 227 * 1024) return false;
+    // occupancy target: 64 registers with the small budget, 128 with the double one
+    const uint32_t minb = std::max<uint32_t>(1, std::min<uint32_t>(8, tmax / threads));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SpecEntry ent;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        SpecKey key{dev, job.prec, n, tpl, w};
+        auto it = g_cache.find(key);
+        if (it == g_cache.end()) {
+            SpecEntry e;
+            e.smem = smem;
+            e.cap = cap;
+            if (compile_spec(job.prec, n, tpl, w, minb, sched, e) && e.kern) {
+                if (cudaFuncSetAttribute((const void *)e.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+                    cudaSuccess) {
+                    cudaGetLastError();
+                    e.kern = nullptr;
+                }
+            } else e.kern = nullptr;
+            it = g_cache.emplace(key, e).first;
+        }
+        ent = it->second;
+    }
+    if (!ent.kern) return false;
+    const void *ptw = get_table(TAB_REGMIX, job.prec, n, cap);
+    uint64_t ntiles;
+    if (job.prec) {
+        TileGeom<double> g;
+        ntiles = fill_geom<double>(g, job, dims, w, load_lf, store_lf);
+        g.ptw = (const double2 *)ptw;
+        void *args[] = {&g};
+        RFB_CUDA_CHECK(cudaLaunchKernel((const void *)ent.kern, dim3((unsigned)ntiles), dim3(threads), args, smem, s));
+    } else {
+        TileGeom<float> g;
+        ntiles = fill_geom<float>(g, job, dims, w, load_lf, store_lf);
+        g.ptw = (const float2 *)ptw;
+        void *args[] = {&g};
+        RFB_CUDA_CHECK(cudaLaunchKernel((const void *)ent.kern, dim3((unsigned)ntiles), dim3(threads), args, smem, s));
+    }
+    count_launch();
+    RFB_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace rfb

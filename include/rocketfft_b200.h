@@ -117,6 +117,42 @@ int rfb200_c2c_scatter(int precision, size_t ndim, const int64_t *shape, const i
                        const int64_t *stride_out, size_t axis, int forward, double fct,
                        const void *d_in, size_t nparts, void *const *d_out_parts, void *stream);
 
+/* ---- (3) the step either side of the path: fused zero-padding / cropping, index rotation ------
+ * The reference's numpy/scipy layer materialises a zero-padded (or cropped) copy of the input before
+ * calling the transform (rocket_fft/overloads.py:575-609, `n` / `s` arguments).  These entry points
+ * take the array as it is (`shape_in`) plus the shape that is to be transformed (`shape`): along
+ * transformed axes the input is cropped to, or zero-extended to, the transform extent while its lines
+ * are loaded; lines that would consist of padding only are never read.  Extents may differ only
+ * along axes listed in `axes`.
+ *   rfb200_c2c_pad: shape_in / shape complex; output has `shape`.
+ *   rfb200_r2c_pad: shape_in / shape real; output has `shape` with axes[naxes-1] -> n/2+1.
+ *   rfb200_c2r_pad: shape_in complex (the bins present), shape = real OUTPUT shape; bins beyond
+ *                   shape_in are zero, bins beyond n/2 along axes[naxes-1] are ignored. */
+int rfb200_c2c_pad(int precision, size_t ndim, const int64_t *shape_in, const int64_t *shape,
+                   const int64_t *stride_in, const int64_t *stride_out, size_t naxes,
+                   const uint64_t *axes, int forward, double fct, const void *d_in, void *d_out,
+                   void *stream);
+int rfb200_r2c_pad(int precision, size_t ndim, const int64_t *shape_in, const int64_t *shape,
+                   const int64_t *stride_in, const int64_t *stride_out, size_t naxes,
+                   const uint64_t *axes, int forward, double fct, const void *d_in, void *d_out,
+                   void *stream);
+int rfb200_c2r_pad(int precision, size_t ndim, const int64_t *shape_in, const int64_t *shape,
+                   const int64_t *stride_in, const int64_t *stride_out, size_t naxes,
+                   const uint64_t *axes, int forward, double fct, const void *d_in, void *d_out,
+                   void *stream);
+/* out[(i + shift[d]) mod shape[d]] = in[i] along every dim d (np.roll; fftshift: shift = n/2,
+ * ifftshift: shift = -(n/2); reference: rocket_fft/overloads.py:752-855, 1221-1310).
+ * itemsize 4, 8 or 16 bytes; in and out must not overlap. */
+int rfb200_roll(int itemsize, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+                const int64_t *stride_out, const int64_t *shift, const void *d_in, void *d_out,
+                void *stream);
+
+/* d_data[l][j] *= d_table[j] for l < nlines, j < n; lines contiguous, items real (complex_items = 0)
+ * or complex (1), precision as above.  The coefficient multiply between the rfft and the irfft of the
+ * fast Hankel transform and its bias factors (reference: rocket_fft/overloads.py:880-901, 1768-1780). */
+int rfb200_scale_lines(int precision, int complex_items, uint64_t nlines, uint64_t n,
+                       const void *d_table, void *d_data, void *stream);
+
 /* ---- housekeeping ----------------------------------------------------------------- */
 /* Last error message of the calling thread ("" if none); cleared by rfb200_clear_error. */
 const char *rfb200_last_error(void);

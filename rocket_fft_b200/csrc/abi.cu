@@ -355,6 +355,75 @@ RFB_EXPORT int rfb200_c2c_scatter(int precision, size_t ndim, const int64_t *sha
     }
 }
 
+// ---- zero-padded / cropped input and index rotation (the layer directly above the path) ---------------
+static int run_pad_op(int kind, int precision, size_t ndim, const int64_t *shape_in, const int64_t *shape,
+                      const int64_t *stride_in, const int64_t *stride_out, size_t naxes, const uint64_t *axes, int forward,
+                      double fct, const void *d_in, void *d_out, void *stream) {
+    clear_error();
+    try {
+        NdArgs a;
+        a.prec = precision ? 1 : 0;
+        a.shape.assign(shape, shape + ndim);
+        a.sin.assign(stride_in, stride_in + ndim);
+        a.sout.assign(stride_out, stride_out + ndim);
+        a.axes.assign(axes, axes + naxes);
+        a.in = (const char *)d_in;
+        a.out = (char *)d_out;
+        a.fct = fct;
+        for (auto ax : a.axes)
+            if (ax >= ndim) { set_error("axis out of range"); throw Error(); }
+        const std::vector<int64_t> sin_shape(shape_in, shape_in + ndim);
+        if (kind == 0) op_c2c_pad(a, sin_shape, forward != 0, (cudaStream_t)stream);
+        else if (kind == 1) op_r2c_pad(a, sin_shape, forward != 0, (cudaStream_t)stream);
+        else op_c2r_pad(a, sin_shape, forward != 0, (cudaStream_t)stream);
+        return 0;
+    } catch (const Error &) {
+        return 1;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return 1;
+    }
+}
+
+#define PAD_ARGS                                                                                                   \
+    int precision, size_t ndim, const int64_t *shape_in, const int64_t *shape, const int64_t *stride_in,           \
+        const int64_t *stride_out, size_t naxes, const uint64_t *axes, int forward, double fct, const void *d_in, \
+        void *d_out, void *stream
+#define PAD_PASS precision, ndim, shape_in, shape, stride_in, stride_out, naxes, axes, forward, fct, d_in, d_out, stream
+RFB_EXPORT int rfb200_c2c_pad(PAD_ARGS) { return run_pad_op(0, PAD_PASS); }
+RFB_EXPORT int rfb200_r2c_pad(PAD_ARGS) { return run_pad_op(1, PAD_PASS); }
+RFB_EXPORT int rfb200_c2r_pad(PAD_ARGS) { return run_pad_op(2, PAD_PASS); }
+
+RFB_EXPORT int rfb200_roll(int itemsize, size_t ndim, const int64_t *shape, const int64_t *stride_in,
+                           const int64_t *stride_out, const int64_t *shift, const void *d_in, void *d_out, void *stream) {
+    clear_error();
+    try {
+        op_roll(itemsize, std::vector<int64_t>(shape, shape + ndim), std::vector<int64_t>(stride_in, stride_in + ndim),
+                std::vector<int64_t>(stride_out, stride_out + ndim), std::vector<int64_t>(shift, shift + ndim),
+                (const char *)d_in, (char *)d_out, (cudaStream_t)stream);
+        return 0;
+    } catch (const Error &) {
+        return 1;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return 1;
+    }
+}
+
+RFB_EXPORT int rfb200_scale_lines(int precision, int complex_items, uint64_t nlines, uint64_t n, const void *d_table,
+                                  void *d_data, void *stream) {
+    clear_error();
+    try {
+        op_scale_lines(precision ? 1 : 0, complex_items != 0, nlines, n, d_table, d_data, (cudaStream_t)stream);
+        return 0;
+    } catch (const Error &) {
+        return 1;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return 1;
+    }
+}
+
 // ---- housekeeping ---------------------------------------------------------------------------------
 RFB_EXPORT const char *rfb200_last_error(void) { return rfb::last_error(); }
 RFB_EXPORT void rfb200_clear_error(void) { rfb::clear_error(); }

@@ -65,10 +65,20 @@ void op_c2c_scatter(const NdArgs &a, size_t axis, bool forward, const std::vecto
 void op_r2c(const NdArgs &a, bool forward, cudaStream_t s);      // shape = real input shape
 void op_c2r(const NdArgs &a, bool forward, cudaStream_t s);      // shape = real output shape
 void op_c2c_sym(const NdArgs &a, bool forward, cudaStream_t s);
+// zero-padded / cropped input fused into the first load (shape_in: the array as it is; a.shape: what is transformed)
+void op_c2c_pad(const NdArgs &a, const std::vector<int64_t> &shape_in, bool forward, cudaStream_t s);
+void op_r2c_pad(const NdArgs &a, const std::vector<int64_t> &shape_in, bool forward, cudaStream_t s);
+void op_c2r_pad(const NdArgs &a, const std::vector<int64_t> &shape_in, bool forward, cudaStream_t s);
+// out[(i + shift) mod n] = in[i] along every dim (fftshift / ifftshift / roll); item: 4, 8 or 16 bytes
+void op_roll(int64_t item, const std::vector<int64_t> &shape, const std::vector<int64_t> &sin,
+             const std::vector<int64_t> &sout, const std::vector<int64_t> &shift, const char *in, char *out, cudaStream_t s);
 void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s);
 void op_fftpack(const NdArgs &a, bool r2h, bool forward, cudaStream_t s);
 void op_separable_hartley(const NdArgs &a, cudaStream_t s);
 void op_genuine_hartley(const NdArgs &a, cudaStream_t s);
+
+// data[l][j] *= table[j] over `nlines` contiguous lines of n items (real or complex, same precision as the table)
+void op_scale_lines(int prec, bool cplx, uint64_t nlines, uint64_t n, const void *table, void *data, cudaStream_t s);
 
 uint64_t launch_count();
 void launch_count_reset();

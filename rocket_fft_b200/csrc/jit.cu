@@ -11,6 +11,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <ctype.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <map>
@@ -97,62 +100,168 @@ struct SpecEntry {
 std::mutex g_mu;
 std::map<SpecKey, SpecEntry> g_cache;
 
-bool compile_spec(int prec, uint64_t n, uint32_t tpl, uint32_t w, uint32_t minb, const std::vector<uint32_t> &sched,
-                  SpecEntry &out) {
+// ---- on-disk cache of compiled cubins (plan persistence across processes) ----------------------------------
+// $RFB200_CACHE_DIR, else $XDG_CACHE_HOME/rocketfft_b200, else $HOME/.cache/rocketfft_b200; RFB200_CACHE_DIR=""
+// disables it.  A file is `<lowered kernel name>\n<cubin bytes>`, named by a hash of the generated source, the
+// compile options and the size + mtime of every kernel header, so a rebuilt library never picks up stale code.
+uint64_t fnv1a(const std::string &s, uint64_t h = 1469598103934665603ull) {
+    for (unsigned char c : s) h = (h ^ c) * 1099511628211ull;
+    return h;
+}
+
+std::string cache_dir() {
+    const char *e = getenv("RFB200_CACHE_DIR");
+    std::string d;
+    if (e) d = e;
+    else if ((e = getenv("XDG_CACHE_HOME")) && *e) d = std::string(e) + "/rocketfft_b200";
+    else if ((e = getenv("HOME")) && *e) d = std::string(e) + "/.cache/rocketfft_b200";
+    if (d.empty()) return d;
+    std::string part;
+    for (size_t i = 0; i <= d.size(); ++i) {  // mkdir -p
+        if (i == d.size() || d[i] == '/') {
+            if (!part.empty()) mkdir(part.c_str(), 0755);
+        }
+        if (i < d.size()) part += d[i];
+    }
+    return d;
+}
+
+std::string header_stamp() {
+    static const std::string stamp = [] {
+        std::string s;
+        const char *files[] = {"spec_kernel.cuh", "common.cuh", "line_io.cuh", "radix.cuh", "tile_kernel.cuh", "modes.h"};
+        const std::string dir = header_dir();
+        for (auto f : files) {
+            struct stat st;
+            if (stat((dir + "/" + f).c_str(), &st) == 0)
+                s += std::string(f) + ":" + std::to_string((long long)st.st_size) + ":" +
+                     std::to_string((long long)st.st_mtime) + ";";
+        }
+        return s;
+    }();
+    return stamp;
+}
+
+bool cache_read(const std::string &path, std::string &lname, std::vector<char> &cubin) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::vector<char> all;
+    char buf[65536];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof(buf), f)) > 0) all.insert(all.end(), buf, buf + k);
+    fclose(f);
+    auto nl = std::find(all.begin(), all.end(), '\n');
+    if (nl == all.end() || all.end() - nl < 64) return false;
+    lname.assign(all.begin(), nl);
+    cubin.assign(nl + 1, all.end());
+    return true;
+}
+
+void cache_write(const std::string &path, const std::string &lname, const std::vector<char> &cubin) {
+    const std::string tmp = path + "." + std::to_string((long long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    bool ok = fwrite(lname.data(), 1, lname.size(), f) == lname.size() && fputc('\n', f) != EOF &&
+              fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    ok = (fclose(f) == 0) && ok;
+    if (ok) rename(tmp.c_str(), path.c_str());  // atomic: concurrent processes see a whole file or none
+    else remove(tmp.c_str());
+}
+
+// NVRTC -> cubin for one plan; *spill = bytes of spill stores ptxas reported
+bool nvrtc_build(const std::string &src, const std::string &name, uint64_t n, std::string &lname, std::vector<char> &cubin,
+                 long *spill) {
     Nvrtc &rt = nvrtc();
     if (!rt.ok) return false;
-    const char *T = prec ? "double" : "float";
-    std::string rad;
-    for (size_t i = 0; i < sched.size(); ++i) rad += (i ? ", " : "") + std::to_string(sched[i]);
-    char src[2048];
-    snprintf(src, sizeof(src),
-             "#include \"spec_kernel.cuh\"\n"
-             "namespace rfb {\n"
-             "struct PJ {\n"
-             "    static constexpr int N = %llu, TPL = %u, W = %u, NPASS = %zu, MINB = %u;\n"
-             "    __host__ __device__ static constexpr int radix(int s) { constexpr int r[%zu] = {%s}; return r[s]; }\n"
-             "};\n"
-             "template __global__ void fft_spec_kernel<%s, PJ, true>(const TileGeom<%s>);\n"
-             "}\n",
-             (unsigned long long)n, tpl, w, sched.size(), minb, sched.size(), rad.c_str(), T, T);
     nvrtcProgram prog = nullptr;
-    if (rt.CreateProgram(&prog, src, "rfb_spec.cu", 0, nullptr, nullptr) != 0) return false;
-    const std::string name = std::string("rfb::fft_spec_kernel<") + T + ", rfb::PJ, true>";
+    if (rt.CreateProgram(&prog, src.c_str(), "rfb_spec.cu", 0, nullptr, nullptr) != 0) return false;
     rt.AddNameExpression(prog, name.c_str());
     const std::string inc = "-I" + header_dir();
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", inc.c_str(), "-default-device", "-lineinfo"};
-    const int rc = rt.CompileProgram(prog, 5, opts);
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", inc.c_str(), "-default-device", "-lineinfo",
+                          "--ptxas-options=-v"};
+    const int rc = rt.CompileProgram(prog, 6, opts);
+    size_t ls = 0;
+    rt.GetProgramLogSize(prog, &ls);
+    std::string log(ls + 1, '\0');
+    rt.GetProgramLog(prog, &log[0]);
     if (rc != 0) {
-        if (getenv("RFB200_JIT_VERBOSE")) {
-            size_t ls = 0;
-            rt.GetProgramLogSize(prog, &ls);
-            std::string log(ls + 1, '\0');
-            rt.GetProgramLog(prog, &log[0]);
+        if (getenv("RFB200_JIT_VERBOSE"))
             fprintf(stderr, "rocketfft_b200: NVRTC failed for n=%llu:\n%s\n", (unsigned long long)n, log.c_str());
-        }
         rt.DestroyProgram(&prog);
         return false;
+    }
+    *spill = 0;
+    const size_t sp = log.find(" bytes spill stores");
+    if (sp != std::string::npos) {
+        size_t b = sp;
+        while (b > 0 && isdigit((unsigned char)log[b - 1])) --b;
+        *spill = atol(log.substr(b, sp - b).c_str());
     }
     const char *lowered = nullptr;
     size_t cs = 0;
     bool ok = rt.GetLoweredName(prog, name.c_str(), &lowered) == 0 && lowered && rt.GetCUBINSize(prog, &cs) == 0 && cs > 0;
-    std::vector<char> cubin(cs);
+    cubin.resize(cs);
     ok = ok && rt.GetCUBIN(prog, cubin.data()) == 0;
-    std::string lname = lowered ? lowered : "";
+    lname = lowered ? lowered : "";
     rt.DestroyProgram(&prog);
-    if (!ok) return false;
-    cudaLibrary_t lib = nullptr;
-    if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+    return ok;
+}
+
+bool compile_spec(int prec, uint64_t n, uint32_t tpl, uint32_t w, uint32_t minb, const std::vector<uint32_t> &sched,
+                  SpecEntry &out) {
+    const char *T = prec ? "double" : "float";
+    const bool verbose = getenv("RFB200_JIT_VERBOSE") != nullptr;
+    std::string rad;
+    for (size_t i = 0; i < sched.size(); ++i) rad += (i ? ", " : "") + std::to_string(sched[i]);
+    const std::string name = std::string("rfb::fft_spec_kernel<") + T + ", rfb::PJ, true>";
+    std::string lname;
+    std::vector<char> cubin;
+    const std::string dir = cache_dir();
+    char key[64];
+    snprintf(key, sizeof(key), "%016llx",
+             (unsigned long long)fnv1a(std::string(T) + "|" + std::to_string(n) + "|" + std::to_string(tpl) + "|" +
+                                       std::to_string(w) + "|" + std::to_string(minb) + "|" + rad + "|" + header_stamp()));
+    const std::string path = dir.empty() ? std::string() : dir + "/spec_" + key + ".cubin";
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        bool have = attempt == 0 && !path.empty() && cache_read(path, lname, cubin);
+        const bool cached = have;
+        if (have && verbose)
+            fprintf(stderr, "rocketfft_b200: jit n=%llu %s from %s\n", (unsigned long long)n, T, path.c_str());
+        // a kernel that spills its register tile is slower than one at half the occupancy target: retry once or twice
+        for (uint32_t mb = minb; !have; mb = mb / 2) {
+            char src[2048];
+            snprintf(src, sizeof(src),
+                     "#include \"spec_kernel.cuh\"\n"
+                     "namespace rfb {\n"
+                     "struct PJ {\n"
+                     "    static constexpr int N = %llu, TPL = %u, W = %u, NPASS = %zu, MINB = %u;\n"
+                     "    __host__ __device__ static constexpr int radix(int s) { constexpr int r[%zu] = {%s}; return r[s]; }\n"
+                     "};\n"
+                     "template __global__ void fft_spec_kernel<%s, PJ, true>(const TileGeom<%s>);\n"
+                     "}\n",
+                     (unsigned long long)n, tpl, w, sched.size(), mb, sched.size(), rad.c_str(), T, T);
+            long spill = 0;
+            if (!nvrtc_build(src, name, n, lname, cubin, &spill)) return false;
+            if (verbose)
+                fprintf(stderr, "rocketfft_b200: jit n=%llu %s tpl=%u w=%u minb=%u [%s] spill=%ld B\n",
+                        (unsigned long long)n, T, tpl, w, mb, rad.c_str(), spill);
+            if (spill <= 64 || mb <= 1) {
+                if (!path.empty()) cache_write(path, lname, cubin);
+                have = true;
+            }
+        }
+        cudaLibrary_t lib = nullptr;
+        cudaKernel_t k = nullptr;
+        if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+            cudaLibraryGetKernel(&k, lib, lname.c_str()) == cudaSuccess && k) {
+            out.kern = k;
+            return true;
+        }
         cudaGetLastError();
-        return false;
+        if (!cached) return false;
+        remove(path.c_str());  // unreadable cache entry: compile afresh
     }
-    cudaKernel_t k = nullptr;
-    if (cudaLibraryGetKernel(&k, lib, lname.c_str()) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    out.kern = k;
-    return true;
+    return false;
 }
 
 }  // namespace
@@ -193,11 +302,12 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
             const uint32_t nb = (uint32_t)(n / R), jmax = e / R;
             t = std::max(t, (nb + jmax - 1) / jmax);
         }
-        const uint32_t tmax = (e == e1) ? 1024u : 512u;
+        // the double budget runs at <= 88 registers per thread: 704 threads still fit one SM's register file
+        const uint32_t tmax = (e == e1) ? 1024u : (lf ? 512u : 704u);
         if (ok && t <= (lf ? tmax / 4 : tmax)) { tpl = t; eb = e; break; }
     }
     if (!tpl) return false;
-    const uint32_t tmax = (eb == e1) ? 1024u : 512u;
+    const uint32_t tmax = (eb == e1) ? 1024u : (lf ? 512u : 704u);
     uint32_t w;
     if (lf) {
         w = (uint32_t)(128 / esz);

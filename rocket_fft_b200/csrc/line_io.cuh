@@ -25,12 +25,14 @@ __device__ __forceinline__ cx<T> load_value(int mode, int flags, const char *lin
             break;
         case LD_HERM: {
             // Hermitian extension of bins 0..n/2; Im of bin 0 (and of bin n/2, n even) ignored
-            // (reference: general_c2r, _pocketfft_hdronly.h:3830, 3845-3846)
+            // (reference: general_c2r, _pocketfft_hdronly.h:3830, 3845-3846); bins >= n_in are zero padding
             const bool upper = 2 * e > n;
             const uint32_t k = upper ? n - e : e;
-            val = ld_cx<T, ALIGNED>(line + (int64_t)k * sa);
-            if (k == 0 || 2 * k == n) val.y = T(0);
-            if (upper) val.y = -val.y;
+            if (k < n_in) {
+                val = ld_cx<T, ALIGNED>(line + (int64_t)k * sa);
+                if (k == 0 || 2 * k == n) val.y = T(0);
+                if (upper) val.y = -val.y;
+            }
             break;
         }
         case LD_HC: {

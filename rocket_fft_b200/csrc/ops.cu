@@ -170,6 +170,250 @@ void op_c2r(const NdArgs &a, bool forward, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Zero-padded / cropped input: the `n` / `s` arguments of the numpy / scipy layer.  The reference
+// materialises a padded copy on the host first (rocket_fft/overloads.py:575-609); here the padding is
+// part of the first load of every line (LineJob::n_in) and lines that consist of padding only are
+// never touched: `valid[d]` is the extent of real data along d, a pass over axis a runs only over the
+// valid extents of the other dims and makes a's extent fully valid.
+// ---------------------------------------------------------------------------------------
+static std::vector<int64_t> valid_extents(const std::vector<int64_t> &shape_in, const std::vector<int64_t> &shape,
+                                          const std::vector<uint64_t> &axes) {
+    if (shape_in.size() != shape.size()) { set_error("input and transform shapes differ in rank"); throw Error(); }
+    std::vector<int64_t> valid(shape.size());
+    for (size_t d = 0; d < shape.size(); ++d) {
+        bool is_axis = false;
+        for (auto ax : axes) is_axis = is_axis || (ax == d);
+        if (!is_axis && shape_in[d] != shape[d]) {
+            set_error("input and transform shapes may differ only along transformed axes");
+            throw Error();
+        }
+        valid[d] = std::min(shape_in[d], shape[d]);
+    }
+    return valid;
+}
+
+static void c2c_axes_pruned(int prec, const std::vector<int64_t> &shape, std::vector<int64_t> valid,
+                            const std::vector<int64_t> &sin, const std::vector<int64_t> &sout, const uint64_t *axes,
+                            size_t naxes, const char *in, char *out, bool forward, double fct, cudaStream_t s) {
+    bool first = true;
+    for (size_t i = 0; i < naxes; ++i) {
+        const size_t ax = (size_t)axes[i];
+        LineJob j;
+        j.prec = prec;
+        j.n = (uint64_t)shape[ax];
+        j.n_in = (uint64_t)valid[ax];
+        j.in = first ? in : out;
+        j.out = out;
+        const auto &si = first ? sin : sout;
+        j.is = si[ax];
+        j.os = sout[ax];
+        j.batch = batch_dims(valid, si, sout, ax);
+        j.backward = !forward;
+        j.fct = first ? fct : 1.0;
+        run_lines(j, s);
+        valid[ax] = shape[ax];
+        first = false;
+    }
+}
+
+// a.shape: the transform (= output) shape
+void op_c2c_pad(const NdArgs &a, const std::vector<int64_t> &shape_in, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape) || any_zero(shape_in) || a.axes.empty()) return;
+    c2c_axes_pruned(a.prec, a.shape, valid_extents(shape_in, a.shape, a.axes), a.sin, a.sout, a.axes.data(),
+                    a.axes.size(), a.in, a.out, forward, a.fct, s);
+}
+
+// a.shape: the (padded / cropped) real shape that is transformed; output extent along axes.back() is n/2+1
+void op_r2c_pad(const NdArgs &a, const std::vector<int64_t> &shape_in, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape) || any_zero(shape_in) || a.axes.empty()) return;
+    std::vector<int64_t> valid = valid_extents(shape_in, a.shape, a.axes);
+    const size_t L = (size_t)a.axes.back();
+    LineJob j;
+    j.prec = a.prec;
+    j.n = (uint64_t)a.shape[L];
+    j.n_in = (uint64_t)valid[L];
+    j.in = a.in;
+    j.out = a.out;
+    j.is = a.sin[L];
+    j.os = a.sout[L];
+    j.batch = batch_dims(valid, a.sin, a.sout, L);
+    j.backward = !forward;
+    j.fct = a.fct;
+    j.load_mode = LD_REAL;
+    j.store_mode = ST_HALF;
+    run_lines(j, s);
+    if (a.axes.size() > 1) {
+        std::vector<int64_t> shape_out = a.shape;
+        shape_out[L] = a.shape[L] / 2 + 1;
+        valid[L] = shape_out[L];
+        c2c_axes_pruned(a.prec, shape_out, valid, a.sout, a.sout, a.axes.data(), a.axes.size() - 1, a.out, a.out, forward,
+                        1.0, s);
+    }
+}
+
+// a.shape: the real output shape; shape_in: the complex input as it is (bins beyond it are zero,
+// bins beyond n/2 along axes.back() are ignored)
+void op_c2r_pad(const NdArgs &a, const std::vector<int64_t> &shape_in, bool forward, cudaStream_t s) {
+    if (any_zero(a.shape) || any_zero(shape_in) || a.axes.empty()) return;
+    const size_t L = (size_t)a.axes.back();
+    const int64_t esz = a.prec ? 16 : 8;
+    std::vector<int64_t> cshape = a.shape;
+    cshape[L] = a.shape[L] / 2 + 1;
+    std::vector<int64_t> valid = valid_extents(shape_in, cshape, a.axes);
+    const char *src = a.in;
+    std::vector<int64_t> ssrc = a.sin;
+    Scratch *tmp = nullptr;
+    struct Guard { Scratch *&p; ~Guard() { delete p; } } guard{tmp};
+    if (a.axes.size() > 1) {
+        // only the bins that exist along L are carried through the leading axes
+        std::vector<int64_t> tshape = cshape;
+        tshape[L] = valid[L];
+        std::vector<int64_t> st = c_strides(tshape, esz);
+        tmp = new Scratch(prod(tshape) * (uint64_t)esz, s);
+        c2c_axes_pruned(a.prec, tshape, valid, a.sin, st, a.axes.data(), a.axes.size() - 1, a.in, (char *)tmp->p, forward,
+                        1.0, s);
+        for (size_t i = 0; i + 1 < a.axes.size(); ++i) valid[a.axes[i]] = tshape[a.axes[i]];
+        src = (const char *)tmp->p;
+        ssrc = st;
+    }
+    LineJob j;
+    j.prec = a.prec;
+    j.n = (uint64_t)a.shape[L];
+    j.n_in = (uint64_t)valid[L];
+    j.in = src;
+    j.out = a.out;
+    j.is = ssrc[L];
+    j.os = a.sout[L];
+    j.batch = batch_dims(a.shape, ssrc, a.sout, L);
+    j.backward = !forward;
+    j.fct = a.fct;
+    j.load_mode = LD_HERM;
+    j.store_mode = ST_REAL;
+    run_lines(j, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// roll: out[(i + shift) mod n] = in[i] along every dim -- fftshift (shift = n/2), ifftshift
+// (shift = -(n/2)) and np.roll of the layer above the path (reference: rocket_fft/overloads.py:752-855,
+// 1221-1310).  One pass over HBM: iteration follows the output (last dim fastest), a thread moves one item.
+// ---------------------------------------------------------------------------------------
+struct RollGeom {
+    int nd;
+    uint32_t ext[8], back[8];  // back = (n - shift) mod n: source index = (j + back) mod n
+    FastDiv d[8];
+    int64_t si[8], so[8];
+};
+
+template <typename V>
+__global__ void __launch_bounds__(256) roll_kernel(const RollGeom g, uint32_t total, const char *__restrict__ in,
+                                                   char *__restrict__ out) {
+    for (uint32_t f = blockIdx.x * 256u + threadIdx.x; f < total; f += gridDim.x * 256u) {
+        uint32_t rem = f;
+        int64_t src = 0, dst = 0;
+#pragma unroll 1
+        for (int d = g.nd - 1; d >= 0; --d) {
+            uint32_t q, j;
+            fdivmod(rem, g.d[d], q, j);
+            rem = q;
+            uint32_t i = j + g.back[d];
+            if (i >= g.ext[d]) i -= g.ext[d];
+            src += (int64_t)i * g.si[d];
+            dst += (int64_t)j * g.so[d];
+        }
+        *reinterpret_cast<V *>(out + dst) = *reinterpret_cast<const V *>(in + src);
+    }
+}
+
+void op_roll(int64_t item, const std::vector<int64_t> &shape, const std::vector<int64_t> &sin,
+             const std::vector<int64_t> &sout, const std::vector<int64_t> &shift, const char *in, char *out,
+             cudaStream_t s) {
+    if (any_zero(shape)) return;
+    if (item != 4 && item != 8 && item != 16) { set_error("roll: item size must be 4, 8 or 16 bytes"); throw Error(); }
+    if (shape.size() != shift.size() || shape.size() != sin.size() || shape.size() != sout.size()) {
+        set_error("roll: shape / strides / shift differ in rank");
+        throw Error();
+    }
+    bool al = ((uintptr_t)in % item) == 0 && ((uintptr_t)out % item) == 0;
+    for (size_t d = 0; d < shape.size(); ++d) al = al && (sin[d] % item) == 0 && (sout[d] % item) == 0;
+    if (!al) { set_error("roll: arrays must be aligned to the item size"); throw Error(); }
+    // drop unit dims; more than 8 dims or >= 2^32 items: peel the outermost dim on the host
+    std::vector<int64_t> sh, si, so, sf;
+    for (size_t d = 0; d < shape.size(); ++d)
+        if (shape[d] > 1) {
+            sh.push_back(shape[d]);
+            si.push_back(sin[d]);
+            so.push_back(sout[d]);
+            sf.push_back(((shift[d] % shape[d]) + shape[d]) % shape[d]);
+        }
+    if (sh.empty()) { sh = {1}; si = {item}; so = {item}; sf = {0}; }
+    if (sh.size() > 8 || prod(sh) >= (1ull << 32) || sh[0] >= (1ll << 32)) {
+        if (sh.size() == 1) { set_error("roll: dimension too long"); throw Error(); }
+        const int64_t n0 = sh[0];
+        std::vector<int64_t> sh1(sh.begin() + 1, sh.end()), si1(si.begin() + 1, si.end()), so1(so.begin() + 1, so.end()),
+            sf1(sf.begin() + 1, sf.end());
+        for (int64_t j = 0; j < n0; ++j) {
+            const int64_t i = (j + n0 - sf[0]) % n0;
+            op_roll(item, sh1, si1, so1, sf1, in + i * si[0], out + j * so[0], s);
+        }
+        return;
+    }
+    RollGeom g;
+    g.nd = (int)sh.size();
+    for (int d = 0; d < g.nd; ++d) {
+        g.ext[d] = (uint32_t)sh[d];
+        g.back[d] = (uint32_t)((sh[d] - sf[d]) % sh[d]);
+        g.d[d] = make_fastdiv((uint32_t)sh[d]);
+        g.si[d] = si[d];
+        g.so[d] = so[d];
+    }
+    const uint32_t total = (uint32_t)prod(sh);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)total + 255) / 256, 148ull * 64);
+    if (item == 4) roll_kernel<uint32_t><<<blocks, 256, 0, s>>>(g, total, in, out);
+    else if (item == 8) roll_kernel<uint2><<<blocks, 256, 0, s>>>(g, total, in, out);
+    else roll_kernel<uint4><<<blocks, 256, 0, s>>>(g, total, in, out);
+    RFB_AFTER_LAUNCH2();
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------
+// data[l][j] *= table[j] for contiguous lines (real x real or complex x complex): the spectral
+// coefficient multiply of the fast Hankel transform and its bias factors (reference:
+// rocket_fft/overloads.py:880-901, 1768-1780: `A *= u`, `a * exp(-bias ...)`)
+// ---------------------------------------------------------------------------------------
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256) scale_lines_kernel(uint64_t nlines, uint32_t n, const T *__restrict__ table,
+                                                          T *__restrict__ data) {
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j >= n) return;
+    if constexpr (CPLX) {
+        using C = cx<T>;
+        const C u = __ldg(reinterpret_cast<const C *>(table) + j);
+        for (uint64_t l = blockIdx.y; l < nlines; l += gridDim.y) {
+            C *p = reinterpret_cast<C *>(data) + l * n + j;
+            *p = cmul(*p, u);
+        }
+    } else {
+        const T u = __ldg(table + j);
+        for (uint64_t l = blockIdx.y; l < nlines; l += gridDim.y) data[l * n + j] *= u;
+    }
+}
+
+void op_scale_lines(int prec, bool cplx, uint64_t nlines, uint64_t n, const void *table, void *data, cudaStream_t s) {
+    if (nlines == 0 || n == 0) return;
+    if (n >= (1ull << 31)) { set_error("scale_lines: line too long"); throw Error(); }
+    const dim3 grid((unsigned)((n + 255) / 256), (unsigned)std::min<uint64_t>(nlines, 16384));
+    if (prec) {
+        if (cplx) scale_lines_kernel<double, true><<<grid, 256, 0, s>>>(nlines, (uint32_t)n, (const double *)table, (double *)data);
+        else scale_lines_kernel<double, false><<<grid, 256, 0, s>>>(nlines, (uint32_t)n, (const double *)table, (double *)data);
+    } else {
+        if (cplx) scale_lines_kernel<float, true><<<grid, 256, 0, s>>>(nlines, (uint32_t)n, (const float *)table, (float *)data);
+        else scale_lines_kernel<float, false><<<grid, 256, 0, s>>>(nlines, (uint32_t)n, (const float *)table, (float *)data);
+    }
+    RFB_AFTER_LAUNCH2();
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------
 // N-D index helper for the mirror / Hartley-combine kernels
 // ---------------------------------------------------------------------------------------
 struct NdIdx {

@@ -100,8 +100,8 @@ bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load
         if (!al && job.is == (int64_t)sizeof(T)) return false;
         mode = 1;
         n /= 2;
-    } else if (job.load_mode == LD_HERM && job.store_mode == ST_REAL && job.flags == 0 && job.twN == 0 && (n % 2 == 0) &&
-               !load_lf && !store_lf && n >= 32) {
+    } else if (job.load_mode == LD_HERM && job.store_mode == ST_REAL && job.flags == 0 && plain_in && job.twN == 0 &&
+               (n % 2 == 0) && !load_lf && !store_lf && n >= 32) {
         mode = 2;
         n /= 2;
     } else if ((job.load_mode == LD_DCT2 && job.store_mode == ST_DCT2) || (job.load_mode == LD_DCT3 && job.store_mode == ST_DCT3)) {

@@ -107,20 +107,30 @@ def _shape_axes(x, s, axes, default_all):
     return s, axes
 
 
-def _pad_or_crop(x, s, axes, dt):
-    x = _as_dtype(x, dt)
+def _target_shape(x, s, axes):
     shape = list(x.shape)
-    changed = False
     for v, a in zip(s, axes):
-        if shape[a] != v:
-            shape[a] = v
-            changed = True
-    if not changed:
+        shape[a] = v
+    return shape
+
+
+def _pad_or_crop(x, s, axes, dt):
+    """Host path / transforms without a fused-padding entry point: cropping is a view, zero-padding a copy
+    (what the reference does for every call, O:575-609)."""
+    x = _as_dtype(x, dt)
+    shape = _target_shape(x, s, axes)
+    if shape == list(x.shape):
         return x
-    out = _zeros(x, shape, dt)
     sl = tuple(slice(0, min(a, b)) for a, b in zip(shape, x.shape))
+    if all(a <= b for a, b in zip(shape, x.shape)):
+        return x[sl]
+    out = _zeros(x, shape, dt)
     out[sl] = x[sl]
     return out
+
+
+def _needs_pad(x, shape):
+    return any(a > b for a, b in zip(shape, x.shape))
 
 
 def _fct(shape, axes, norm, forward, delta=None):
@@ -144,6 +154,12 @@ def _c2cn(x, s, axes, norm, forward, default_all):
     dt = _np_dtype(x)
     cdt = _cplx_of(dt)
     if _is_complex(dt):
+        shape = _target_shape(x, s, axes)
+        if _is_torch(x) and _needs_pad(x, shape):
+            # device arrays: zero-padding is part of the first load of every line (rfb200_c2c_pad)
+            out = _empty(x, shape, cdt)
+            _ll.c2c_pad(_as_dtype(x, cdt), out, axes, forward, _fct(shape, axes, norm, forward))
+            return out
         x = _pad_or_crop(x, s, axes, cdt)
         out = _empty(x, x.shape, cdt)
         _ll.c2c(x, out, axes, forward, _fct(x.shape, axes, norm, forward))
@@ -160,6 +176,13 @@ def _r2cn(x, s, axes, norm, forward, default_all):
         raise TypeError(f"unsupported dtype {dt}")
     s, axes = _shape_axes(x, s, axes, default_all)
     rdt = _real_of(dt)
+    full = _target_shape(x, s, axes)
+    if _is_torch(x) and _needs_pad(x, full):
+        shape = list(full)
+        shape[axes[-1]] = full[axes[-1]] // 2 + 1
+        out = _empty(x, shape, _cplx_of(rdt))
+        _ll.r2c_pad(_as_dtype(x, rdt), out, full, axes, forward, _fct(full, axes, norm, forward))
+        return out
     x = _pad_or_crop(x, s, axes, rdt)
     shape = list(x.shape)
     shape[axes[-1]] = shape[axes[-1]] // 2 + 1
@@ -178,6 +201,12 @@ def _c2rn(x, s, axes, norm, forward, default_all):
         raise ValueError(f"Invalid number of data points ({n_last}) specified")
     s_in = list(s)
     s_in[-1] = n_last // 2 + 1
+    if _is_torch(x) and _needs_pad(x, _target_shape(x, s_in, axes)):
+        shape = _target_shape(x, s, axes)
+        shape[last] = n_last
+        out = _empty(x, shape, _real_of(cdt))
+        _ll.c2r_pad(_as_dtype(x, cdt), out, axes, forward, _fct(shape, axes, norm, forward))
+        return out
     xin = _pad_or_crop(x, s_in, axes, cdt)
     shape = list(xin.shape)
     shape[last] = n_last
@@ -317,3 +346,104 @@ def next_fast_len(target, real=False):
     if target < 0:
         raise ValueError("Target cannot be negative.")
     return _ll.good_size(int(target), bool(real))
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers either side of a transform (reference: rocket_fft/overloads.py:752-855, 1221-1310)
+# ---------------------------------------------------------------------------------------------
+def _roll_axes(x, axes, sign):
+    nd = len(x.shape)
+    if axes is None:
+        axes = list(range(nd))
+    elif not hasattr(axes, "__len__"):
+        axes = [int(axes)]
+    shift = [0] * nd
+    for a in axes:
+        a = int(a)
+        if not -nd <= a < nd:
+            raise ValueError("axes exceeds dimensionality of input")
+        shift[a % nd] += sign * (x.shape[a % nd] // 2)
+    return roll(x, shift, axis=list(range(nd)))
+
+
+def roll(x, shift, axis=None):
+    """numpy.roll: a single pass of the index-rotation kernel (rfb200_roll).  NumPy inputs are staged through
+    device memory (H2D, kernel, D2H); torch CUDA tensors stay on the device."""
+    import torch
+
+    host = not _is_torch(x)
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda() if host else x
+    nd = xd.dim()
+    if axis is None:
+        flat = xd.reshape(-1)
+        out = torch.empty_like(flat)
+        total = int(np.sum(shift)) if hasattr(shift, "__len__") else int(shift)
+        _roll_any(flat, out, [total])
+        out = out.reshape(xd.shape)
+    else:
+        axes = [int(a) for a in (axis if hasattr(axis, "__len__") else [axis])]
+        shifts = [int(v) for v in (shift if hasattr(shift, "__len__") else [shift] * len(axes))]
+        if len(shifts) != len(axes):
+            raise ValueError("shift and axis must have the same length")
+        per = [0] * nd
+        for a, v in zip(axes, shifts):
+            if not -nd <= a < nd:
+                raise ValueError("axis out of range")
+            per[a % nd] += v
+        out = torch.empty(xd.shape, dtype=xd.dtype, device=xd.device)
+        _roll_any(xd, out, per)
+    return out.cpu().numpy() if host else out
+
+
+def _roll_any(x, out, per):
+    import torch
+
+    item = x.element_size()
+    if item in (4, 8, 16):
+        _ll.roll(x, out, per)
+        return
+    if x.numel() == 0:
+        return
+    # 1- and 2-byte items: move them as 4-byte words when the last dim allows it, else widen
+    wide = x.to(torch.float32 if x.is_floating_point() else torch.int32)
+    tmp = torch.empty_like(wide)
+    _ll.roll(wide, tmp, per)
+    out.copy_(tmp.to(x.dtype))
+
+
+def fftshift(x, axes=None):
+    """Zero-frequency bin to the centre: out[(i + n//2) mod n] = x[i] along `axes` (all by default)."""
+    return _roll_axes(x, axes, +1)
+
+
+def ifftshift(x, axes=None):
+    """Inverse of fftshift: out[(i - n//2) mod n] = x[i]."""
+    return _roll_axes(x, axes, -1)
+
+
+def fftfreq(n, d=1.0, device=None):
+    """Sample frequencies [0, 1, ..., (n-1)//2, -(n//2), ..., -1] / (d n) (float64); on `device` if given."""
+    n = int(n)
+    if n < 1:
+        raise ValueError(f"n should be an integer greater than 0, got {n}")
+    k = np.arange(n, dtype=np.int64)
+    k[(n - 1) // 2 + 1:] -= n
+    out = k * (1.0 / (n * d))  # same rounding as numpy: multiply by the reciprocal
+    if device is not None:
+        import torch
+
+        return torch.from_numpy(out).to(device)
+    return out
+
+
+def rfftfreq(n, d=1.0, device=None):
+    """Sample frequencies [0, 1, ..., n//2] / (d n) (float64); on `device` if given."""
+    n = int(n)
+    if n < 1:
+        raise ValueError(f"n should be an integer greater than 0, got {n}")
+    out = np.arange(n // 2 + 1, dtype=np.int64) * (1.0 / (n * d))
+    if device is not None:
+        import torch
+
+        return torch.from_numpy(out).to(device)
+    return out

@@ -244,6 +244,114 @@ def c2c_scatter(ain, parts, axis, forward, fct):
     return parts
 
 
+_PAD_ARGS = [C.c_int, C.c_size_t, _I64P, _I64P, _I64P, _I64P, C.c_size_t, _U64P, C.c_int, C.c_double,
+             C.c_void_p, C.c_void_p, C.c_void_p]
+for _name in ("rfb200_c2c_pad", "rfb200_r2c_pad", "rfb200_c2r_pad"):
+    getattr(_c, _name).restype = C.c_int
+    getattr(_c, _name).argtypes = _PAD_ARGS
+_c.rfb200_roll.restype = C.c_int
+_c.rfb200_roll.argtypes = [C.c_int, C.c_size_t, _I64P, _I64P, _I64P, _I64P, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+def _pad_call(op, ain, aout, shape, axes, forward, fct):
+    """Device arrays only: `ain` as it is, `shape` what is transformed (see include/rocketfft_b200.h (3))."""
+    base = op[:-4]
+    prec = _check(base, ain, aout)
+    pin, shp_in, st_in, _, dev_in, _k1 = _abi.describe(ain)
+    pout, shp_out, st_out, _, dev_out, _k2 = _abi.describe(aout)
+    if not (dev_in and dev_out):
+        raise TypeError(f"{op} works on device arrays")
+    nd = len(shp_in)
+    shape = tuple(int(v) for v in shape)
+    if len(shp_out) != nd or len(shape) != nd:
+        raise ValueError("Input, output and transform shape must have the same number of dimensions")
+    ax = [int(a) for a in np.asarray(axes).ravel()]
+    for a in ax:
+        if not 0 <= a < nd:
+            raise ValueError("axis out of range")
+    want_out = list(shape)
+    if base == "r2c" and ax:
+        want_out[ax[-1]] = shape[ax[-1]] // 2 + 1
+    if tuple(want_out) != tuple(shp_out):
+        raise ValueError(f"{op}: output shape {tuple(shp_out)} does not match the transform shape {tuple(want_out)}")
+    A = (C.c_int64 * max(nd, 1))
+    rc = getattr(_c, "rfb200_" + op)(
+        prec, nd, A(*shp_in), A(*shape), A(*st_in), A(*st_out), len(ax), (C.c_uint64 * max(len(ax), 1))(*ax),
+        int(bool(forward)), float(fct), C.c_void_p(pin), C.c_void_p(pout), C.c_void_p(_current_stream()),
+    )
+    if rc != 0:
+        raise TransformError(last_error())
+    return aout
+
+
+def c2c_pad(ain, aout, axes, forward, fct):
+    """c2c of `ain` cropped / zero-extended to aout's shape along `axes`, without a padded copy."""
+    return _pad_call("c2c_pad", ain, aout, _abi.describe(aout)[1], axes, forward, fct)
+
+
+def r2c_pad(ain, aout, shape, axes, forward, fct):
+    """r2c of the real array `ain` cropped / zero-extended to `shape` (the real transform shape)."""
+    return _pad_call("r2c_pad", ain, aout, shape, axes, forward, fct)
+
+
+def c2r_pad(ain, aout, axes, forward, fct):
+    """c2r producing `aout` (its shape is the transform shape) from the bins present in `ain`."""
+    return _pad_call("c2r_pad", ain, aout, _abi.describe(aout)[1], axes, forward, fct)
+
+
+def roll(ain, aout, shift):
+    """aout[(i + shift[d]) mod n_d] = ain[i] along every dim (device arrays; 4/8/16-byte items)."""
+    pin, shp_in, st_in, item, dev_in, _k1 = _abi.describe(ain)
+    pout, shp_out, st_out, item2, dev_out, _k2 = _abi.describe(aout)
+    if not (dev_in and dev_out):
+        raise TypeError("roll works on device arrays")
+    if tuple(shp_in) != tuple(shp_out) or item != item2:
+        raise ValueError("roll: input and output must have the same shape and item size")
+    nd = len(shp_in)
+    sh = [int(v) for v in shift]
+    if len(sh) != nd:
+        raise ValueError("roll: one shift per dimension")
+    A = (C.c_int64 * max(nd, 1))
+    rc = _c.rfb200_roll(int(item), nd, A(*shp_in), A(*st_in), A(*st_out), A(*sh), C.c_void_p(pin), C.c_void_p(pout),
+                        C.c_void_p(_current_stream()))
+    if rc != 0:
+        raise TransformError(last_error())
+    return aout
+
+
+_c.rfb200_scale_lines.restype = C.c_int
+_c.rfb200_scale_lines.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+def scale_lines(data, table):
+    """data[..., j] *= table[j] in place; `data` a contiguous device array, `table` a contiguous 1-D device array of
+    the same dtype (float32/64 or complex64/128) and of data's last extent."""
+    pd, shp, st, item, dev, _k1 = _abi.describe(data)
+    pt, tshp, tst, titem, tdev, _k2 = _abi.describe(table)
+    dt = _abi.dtype_of(data)
+    if not (dev and tdev) or dt != _abi.dtype_of(table) or dt not in _REAL + _CPLX:
+        raise TypeError("scale_lines: device arrays of one real or complex floating dtype expected")
+    n = shp[-1] if shp else 1
+    acc = item
+    for ext, sb in zip(reversed(shp), reversed(st)):
+        if ext > 1 and sb != acc:
+            raise ValueError("scale_lines: data must be C-contiguous")
+        acc *= max(ext, 1)
+    if tuple(tshp) != (n,) or (n > 1 and tst[0] != titem):
+        raise ValueError("scale_lines: table must be contiguous with data's last extent")
+    total = 1
+    for ext in shp:
+        total *= ext
+    if total == 0:
+        return data
+    prec = 0 if dt in (np.dtype(np.float32), np.dtype(np.complex64)) else 1
+    rc = _c.rfb200_scale_lines(prec, int(dt in _CPLX), total // n, n, C.c_void_p(pt), C.c_void_p(pd),
+                               C.c_void_p(_current_stream()))
+    if rc != 0:
+        raise TransformError(last_error())
+    return data
+
+
 def good_size(n, real):
     return lib.good_size(n, real)
 

@@ -1,0 +1,66 @@
+"""Run in a subprocess with RFB200_JIT=2 (every eligible length goes through the NVRTC-specialised kernel)
+and RFB200_JIT_VERBOSE=1: compares a set of smooth non-power-of-two transforms with the oracle
+(the compiled reference when oracle/_ref is present, else the numpy restatement).  Exits non-zero on mismatch."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np
+
+import parity
+import rocket_fft_b200 as R
+from oracle import pocketfft_oracle as O
+
+T = parity.reflib() or O
+rng = np.random.default_rng(11)
+bad = 0
+
+
+def check(name, got, want, dtype, n):
+    global bad
+    e = parity.l2err(got, want)
+    t = parity.tol(dtype, n)
+    ok = e <= t
+    bad += not ok
+    print(f"{'ok ' if ok else 'BAD'} {name}: err {e:.2e} tol {t:.2e}", flush=True)
+
+
+for dt in (np.complex64, np.complex128):
+    for n in (6, 96, 100, 360, 1000, 1920, 3000, 6561, 15015):
+        if dt == np.complex128 and n > 6561:
+            continue
+        rows = 5
+        x = (rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))).astype(dt)
+        for fwd in (True, False):
+            got, want = np.empty_like(x), np.empty_like(x)
+            R.c2c(x, got, [1], fwd, 0.5)
+            T.c2c(x, want, [1], fwd, 0.5, 1)
+            check(f"c2c {np.dtype(dt).name} n={n} fwd={fwd}", got, want, dt, n)
+    # strided lines (columns) and in-place
+    x = (rng.standard_normal((360, 37)) + 1j * rng.standard_normal((360, 37))).astype(dt)
+    want = np.empty_like(x)
+    T.c2c(x, want, [0], True, 1.0, 1)
+    got = x.copy()
+    R.c2c(got, got, [0], True, 1.0)
+    check(f"c2c columns in-place {np.dtype(dt).name} (360,37)", got, want, dt, 360)
+# real transforms on jitted lengths
+for dt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
+    for n in (1000, 1001, 1920):
+        x = rng.standard_normal((7, n)).astype(dt)
+        got = np.zeros((7, n // 2 + 1), dtype=cdt)
+        want = np.zeros_like(got)
+        R.r2c(x, got, [1], True, 1.0)
+        T.r2c(x, want, [1], True, 1.0, 1)
+        check(f"r2c {np.dtype(dt).name} n={n}", got, want, dt, n)
+        back, wback = np.empty_like(x), np.empty_like(x)
+        R.c2r(want, back, [1], False, 1.0 / n)
+        T.c2r(want, wback, [1], False, 1.0 / n, 1)
+        check(f"c2r {np.dtype(dt).name} n={n}", back, wback, dt, n)
+    x = rng.standard_normal((1080, 48)).astype(dt)
+    got, want = np.empty_like(x), np.empty_like(x)
+    R.r2r_separable_hartley(x, got, [0, 1], 1.0)
+    T.r2r_separable_hartley(x, want, [0, 1], 1.0, 1)
+    check(f"hartley {np.dtype(dt).name} (1080,48)", got, want, dt, 1080 * 48)
+print("launches", R.launch_count())
+sys.exit(1 if bad else 0)

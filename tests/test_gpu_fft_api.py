@@ -105,3 +105,85 @@ def test_torch_device_tensors(F):
     d = F.dctn(x.double(), axes=(1,))
     want = scipy.fft.dctn(x.double().cpu().numpy(), axes=(1,))
     assert parity.l2err(d.cpu().numpy(), want) < 1e-11
+
+
+def test_fused_padding_and_cropping_on_device(F):
+    """`n` / `s` on device tensors: zero-padding happens in the first load of every line (rfb200_*_pad),
+    cropping is a strided view -- same results as SciPy's pad-then-transform (reference: O:575-609)."""
+    import torch
+
+    import rocket_fft_b200 as R
+
+    rng = np.random.default_rng(5)
+    for dt, tolv in ((np.complex128, 1e-11), (np.complex64, 2e-5)):
+        rdt = np.float64 if dt == np.complex128 else np.float32
+        x = (rng.standard_normal((6, 42, 10)) + 1j * rng.standard_normal((6, 42, 10))).astype(dt)
+        xr = rng.standard_normal((6, 42, 10)).astype(rdt)
+        d, dr = torch.from_numpy(x).cuda(), torch.from_numpy(xr).cuda()
+        for norm in (None, "ortho"):
+            for n in (8, 42, 55, 64, 100, 128, 4096):
+                for axis in (-1, 0, 1):
+                    close(F.fft(d, n, axis, norm).cpu().numpy(), scipy.fft.fft(x, n, axis, norm), tolv)
+                    close(F.ifft(d, n, axis, norm).cpu().numpy(), scipy.fft.ifft(x, n, axis, norm), tolv)
+                    close(F.rfft(dr, n, axis, norm).cpu().numpy(), scipy.fft.rfft(xr, n, axis, norm), tolv)
+                    close(F.irfft(d, n, axis, norm).cpu().numpy(), scipy.fft.irfft(x, n, axis, norm), tolv)
+                    close(F.hfft(d, n, axis, norm).cpu().numpy(), scipy.fft.hfft(x, n, axis, norm), tolv)
+                    close(F.ihfft(dr, n, axis, norm).cpu().numpy(), scipy.fft.ihfft(xr, n, axis, norm), tolv)
+            for s, axes in (((8, 12), (0, 1)), ((7, 50, 3), None), ((9, 64, 16), None), ((64,), (1,)), ((12, 3), (2, 0)),
+                            ((16, 60), (0, 1)), ((3, 128), (1, 2))):
+                close(F.fftn(d, s, axes, norm).cpu().numpy(), scipy.fft.fftn(x, s, axes, norm), tolv)
+                close(F.ifftn(d, s, axes, norm).cpu().numpy(), scipy.fft.ifftn(x, s, axes, norm), tolv)
+                close(F.rfftn(dr, s, axes, norm).cpu().numpy(), scipy.fft.rfftn(xr, s, axes, norm), tolv)
+                close(F.irfftn(d, s, axes, norm).cpu().numpy(), scipy.fft.irfftn(x, s, axes, norm), tolv)
+    # a padded transform launches no copy / fill kernels: one line kernel per axis
+    big = torch.randn(64, 1000, dtype=torch.complex64, device="cuda")
+    R.launch_count_reset()
+    F.fft(big, 2048, -1)
+    assert R.launch_count() == 1
+    # long padded lines (four-step / gather path) and a non-contiguous input
+    x = (rng.standard_normal((3, 70000)) + 1j * rng.standard_normal((3, 70000))).astype(np.complex128)
+    d = torch.from_numpy(x).cuda()
+    close(F.fft(d, 131072, -1).cpu().numpy(), scipy.fft.fft(x, 131072, -1), 1e-11)
+    close(F.fft(d.t(), 100, 1).cpu().numpy(), scipy.fft.fft(x.T, 100, 1), 1e-11)
+    # shapes that differ along an untransformed axis are rejected
+    with pytest.raises(R.TransformError):
+        R.c2c_pad(d, torch.empty(4, 70000, dtype=torch.complex128, device="cuda"), [1], True, 1.0)
+
+
+def test_shift_roll_and_frequencies(F):
+    """fftshift / ifftshift / roll are one pass of the rotation kernel: bit-exact against NumPy
+    (reference: rocket_fft/overloads.py:752-855, 1221-1310)."""
+    import torch
+
+    import rocket_fft_b200 as R
+
+    rng = np.random.default_rng(6)
+    for shape in ((1,), (7,), (8,), (5, 6), (4, 1, 9), (3, 4, 5, 6), (2, 3, 2, 3, 2, 3, 2, 3, 2)):
+        for dt in (np.float32, np.float64, np.complex64, np.complex128, np.int32, np.int64, np.float16, np.int8):
+            x = (rng.standard_normal(shape) * 100).astype(dt)
+            if np.dtype(dt).kind == "c":
+                x = x + 1j * (rng.standard_normal(shape) * 100).astype(dt)
+            d = torch.from_numpy(x).cuda()
+            nd = len(shape)
+            for axes in (None, 0, -1, tuple(range(nd)), (0, 0), (nd - 1, 0)):
+                assert np.array_equal(F.fftshift(d, axes).cpu().numpy(), np.fft.fftshift(x, axes))
+                assert np.array_equal(F.ifftshift(d, axes).cpu().numpy(), np.fft.ifftshift(x, axes))
+            assert np.array_equal(F.fftshift(x), np.fft.fftshift(x))      # host arrays are staged
+            for shift, axis in ((3, None), (-2, 0), ((1, -5), (0, nd - 1)), (10 ** 6 + 1, -1)):
+                assert np.array_equal(F.roll(d, shift, axis).cpu().numpy(), np.roll(x, shift, axis))
+    # strided input / output through the low-level call, large array (> 2^32 bytes is peeled on the host)
+    x = torch.randn(512, 1000, device="cuda")
+    out = torch.empty(1000, 512, device="cuda").t()
+    R.roll(x.t().contiguous().t(), out, [256, 500])
+    assert torch.equal(out, torch.roll(x, (256, 500), (0, 1)))
+    big = torch.arange(1 << 26, dtype=torch.float32, device="cuda").reshape(8192, 8192)
+    assert torch.equal(F.fftshift(big), torch.fft.fftshift(big))
+    with pytest.raises(ValueError):
+        F.fftshift(big, axes=2)
+    for n in (1, 2, 7, 8, 1001):
+        for dd in (1.0, 0.25):
+            assert np.array_equal(F.fftfreq(n, dd), np.fft.fftfreq(n, dd))
+            assert np.array_equal(F.rfftfreq(n, dd), np.fft.rfftfreq(n, dd))
+    assert F.fftfreq(8, device="cuda").is_cuda
+    with pytest.raises(ValueError):
+        F.fftfreq(0)

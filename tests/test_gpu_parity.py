@@ -5,6 +5,7 @@ compiled reference (oracle/_ref, when it travelled with the snapshot), the NumPy
 and the committed golden vectors.  Tolerance: rel-L2 <= 1e-5*log2(n) (fp32),
 1e-13*log2(n) (fp64), n = product of the transformed lengths (north-star bound)."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -464,3 +465,20 @@ def test_bluestein_strided_and_batched(R, dt):
     R.r2c(xr, a, [1], True, 1.0)
     T.r2c(xr, b, [1], True, 1.0)
     check(a, b, dt, 4099, "r2c prime")
+
+
+def test_runtime_specialised_kernels(tmp_path):
+    """Smooth non-power-of-two lengths through the NVRTC-specialised kernel (csrc/jit.cu, RFB200_JIT=2 forces
+    it for every eligible call), twice: the second process must take its cubins from the on-disk cache."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, RFB200_JIT="2", RFB200_JIT_VERBOSE="1", RFB200_CACHE_DIR=str(tmp_path / "jitcache"))
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_jit_check.py")
+    first = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
+    assert first.returncode == 0, first.stdout[-3000:] + first.stderr[-3000:]
+    assert "rocketfft_b200: jit n=1000 float" in first.stderr, first.stderr[-2000:]
+    assert "spill=" in first.stderr
+    second = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
+    assert second.returncode == 0, second.stdout[-3000:] + second.stderr[-3000:]
+    assert " from " in second.stderr and "spill=" not in second.stderr, second.stderr[-2000:]

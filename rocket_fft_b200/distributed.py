@@ -13,6 +13,9 @@ Two ways the transform path shards:
   The result is left in the TRANSPOSED distribution (axis 1 sharded, axis 0 complete),
   which is what a following inverse transform wants; `transpose_back=True` adds the second
   all-to-all that restores the input distribution.
+* the real counterpart (`SlabRFFTN`): rfftn of a real volume = r2c along axis 2 on the
+  slab, then the complex pipeline above on the half-spectrum volume (N0, N1, N2/2+1); irfftn runs it backwards
+  from the transposed distribution (c2c along axis 0, exchange, c2r over axes (1, 2)).
 """
 from __future__ import annotations
 
@@ -182,3 +185,78 @@ class SlabFFTN:
         for s in shape:
             n *= int(s)
         return 5.0 * n * math.log2(n)
+
+
+class SlabRFFTN:
+    """rfftn / irfftn of a 3-D real volume sharded by slabs of axis 0.
+
+    forward(x):  x = this rank's real slab (n0/P, n1, n2)  ->  its part (n0, n1/P, n2//2+1) of rfftn(X),
+                 axis 1 sharded (the transposed distribution, as SlabFFTN leaves it).
+    inverse(Y):  Y = (n0, n1/P, n2//2+1) in that distribution  ->  real slab (n0/P, n1, n2) of irfftn.
+    Semantics per axis are those of the single-device path (r2c / c2r, _pocketfft_hdronly.h:3955-4023):
+    the real transform runs along the LAST axis, c2c along the others.
+    `local` = (r2c, c2r, c2c) single-device callables, default: rocket_fft_b200 on CUDA tensors.
+    """
+
+    def __init__(self, shape, dtype, device, group=None, local=None, dist=None, exchange="auto"):
+        import torch
+
+        n0, n1, n2 = (int(s) for s in shape)
+        self.shape = (n0, n1, n2)
+        self.n2h = n2 // 2 + 1
+        self.rdtype = dtype
+        self.cdtype = {torch.float32: torch.complex64, torch.float64: torch.complex128}[dtype]
+        if local is None:
+            from . import lowlevel
+
+            local = (lowlevel.r2c, lowlevel.c2r, None)
+        self.r2c, self.c2r, c2c = local
+        self.inner = SlabFFTN((n0, n1, self.n2h), self.cdtype, device, group=group, local_c2c=c2c, dist=dist,
+                              exchange=exchange)
+        self.P, self.rank = self.inner.P, self.inner.rank
+        self.torch = torch
+        self.spec = torch.empty((n0 // self.P, n1, self.n2h), dtype=self.cdtype, device=device)
+        self.bytes_sent_per_rank = self.inner.bytes_sent_per_rank
+
+    @property
+    def mode(self):
+        return self.inner.mode
+
+    def forward(self, x, forward=True, fct=1.0):
+        """Real slab in (left untouched), complex (n0, n1/P, n2//2+1) out (a view of the plan's receive buffer)."""
+        inner = self.inner
+        self.r2c(x, self.spec, [2], forward, fct)                      # real transform along the last axis
+        if inner.mode == "fused":
+            inner.scatter_axis1(self.spec, forward)                    # axis-1 transform + all-to-all push
+        else:
+            inner.c2c(self.spec, self.spec, [1], forward, 1.0)
+            inner.exchange(self.spec)
+        return inner.local_axis0(forward)
+
+    def inverse(self, y, out=None, forward=False, fct=None):
+        """y: (n0, n1/P, n2//2+1) complex, overwritten.  Returns the real slab (n0/P, n1, n2);
+        fct defaults to 1/(n0 n1 n2) (numpy's irfftn)."""
+        inner, P = self.inner, self.P
+        n0, n1, n2 = self.shape
+        n1p = n1 // P
+        if fct is None:
+            fct = 1.0 / (float(n0) * n1 * n2)
+        inner.c2c(y, y, [0], forward, 1.0)
+        # exchange back: block (h -> g) = axis-0 range of g x axis-1 range of h
+        send = y.reshape(P, n0 // P, n1p, self.n2h)
+        if not send.is_contiguous():
+            send = send.contiguous()
+        back = self.torch.empty_like(send)
+        inner.dist.all_to_all_single(back.view(-1), send.view(-1), group=inner.group)
+        self.spec.view(n0 // P, P, n1p, self.n2h).copy_(back.permute(1, 0, 2, 3))
+        if out is None:
+            out = self.torch.empty((n0 // P, n1, n2), dtype=self.rdtype, device=self.spec.device)
+        self.c2r(self.spec, out, [1, 2], forward, fct)                # c2c along axis 1, Hermitian -> real along 2
+        return out
+
+    @staticmethod
+    def flops(shape):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        return 2.5 * n * math.log2(n)

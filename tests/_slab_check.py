@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 
 import rocket_fft_b200 as R
-from rocket_fft_b200.distributed import SlabFFTN, shard_batch
+from rocket_fft_b200.distributed import SlabFFTN, SlabRFFTN, shard_batch
 
 rank = int(os.environ["RANK"])
 world = int(os.environ["WORLD_SIZE"])
@@ -33,6 +33,20 @@ for shape in ((128, 128, 128), (64, 96, 40)):
     tol = 1e-5 * 21
     print(f"rank {rank} shape {shape} err {err:.3e} {err2:.3e}", flush=True)
     ok = ok and err < tol and err2 < tol
+# real volumes: rfftn into the transposed distribution and irfftn back
+for shape in ((128, 128, 128), (64, 96, 41)):
+    g = torch.Generator(device=dev).manual_seed(8)
+    full = torch.randn(*shape, dtype=torch.float32, device=dev, generator=g)
+    lo, hi = shard_batch(shape[0], rank, world)
+    plan = SlabRFFTN(shape, torch.float32, dev, exchange="auto" if shape[1] == 128 else "symm")
+    y = plan.forward(full[lo:hi].contiguous())
+    want = torch.fft.rfftn(full)
+    j0, j1 = shard_batch(shape[1], rank, world)
+    err = float(torch.linalg.vector_norm((y - want[:, j0:j1]).to(torch.complex128)) / torch.linalg.vector_norm(want[:, j0:j1].to(torch.complex128)))
+    back = plan.inverse(y.clone())
+    err2 = float(torch.linalg.vector_norm((back - full[lo:hi]).double()) / torch.linalg.vector_norm(full[lo:hi].double()))
+    print(f"rank {rank} real {shape} mode {plan.mode} err {err:.3e} {err2:.3e}", flush=True)
+    ok = ok and err < 1e-5 * 21 and err2 < 1e-5 * 21
 # batch sharding: every rank transforms its rows; concatenation equals the full transform
 rows = 64
 g = torch.Generator(device=dev).manual_seed(9)

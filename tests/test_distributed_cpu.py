@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from rocket_fft_b200.distributed import SlabFFTN, shard_batch
+from rocket_fft_b200.distributed import SlabFFTN, SlabRFFTN, shard_batch
 
 
 def _free_port():
@@ -70,6 +70,56 @@ def test_slab_fftn_world2_gloo(transpose_back):
     for rank, err, sent in res:
         assert err < 1e-13, (rank, err)
         assert sent == 8 * 6 * 10 * 16 // 2 // 2
+
+
+def _oracle_real(kind):
+    def run(a, b, axes, fwd, fct):
+        from oracle import pocketfft_oracle as O
+
+        out = np.empty(tuple(b.shape), dtype=b.numpy().dtype)
+        getattr(O, kind)(np.ascontiguousarray(a.numpy()), out, axes, fwd, fct)
+        b.copy_(torch.from_numpy(out))
+        return b
+
+    return run
+
+
+def _worker_real(rank, world, port, shape, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(6)
+        full = rng.standard_normal(shape)
+        lo, hi = shard_batch(shape[0], rank, world)
+        x = torch.from_numpy(full[lo:hi].copy())
+        plan = SlabRFFTN(shape, torch.float64, "cpu", local=(_oracle_real("r2c"), _oracle_real("c2r"), _oracle_c2c))
+        y = plan.forward(x)
+        want = np.fft.rfftn(full)
+        j0, j1 = shard_batch(shape[1], rank, world)
+        err = np.linalg.norm(y.numpy() - want[:, j0:j1]) / np.linalg.norm(want[:, j0:j1])
+        back = plan.inverse(y.clone())
+        err2 = np.linalg.norm(back.numpy() - full[lo:hi]) / np.linalg.norm(full[lo:hi])
+        q.put((rank, float(err), float(err2), tuple(y.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(8, 6, 10), (4, 10, 9)])
+def test_slab_rfftn_irfftn_world2_gloo(shape):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_real, args=(r, 2, port, shape, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, err2, yshape in res:
+        assert yshape == (shape[0], shape[1] // 2, shape[2] // 2 + 1)
+        assert err < 1e-13 and err2 < 1e-13, (rank, err, err2)
 
 
 def test_shard_batch_covers_everything():

@@ -1,8 +1,10 @@
 // Host-side construction of the kernel geometry shared by the tile kernel and the
 // power-of-two kernel launchers.
 #pragma once
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "engine.h"
@@ -75,6 +77,64 @@ inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<
         g.twB = (const cx<T> *)get_table(TAB_SPLIT_B, job.prec, job.twN, S);
     }
     return ntiles;
+}
+
+// L2 prefetch of a later tile's input (prefetch_later_tile in tile_kernel.cuh): for element-fast tiles whose W lines of
+// `n_items` items of `item` bytes form one (nearly) dense run of bytes.  RFB200_PF = distance in tiles, 0 = off.
+template <typename T>
+inline void set_prefetch(TileGeom<T> &g, const LineJob &job, const std::vector<Dim> &dims, uint32_t W, int64_t item,
+                         uint64_t n_items) {
+    static const int pf = [] {
+        const char *v = getenv("RFB200_PF");
+        return v ? atoi(v) : 148;
+    }();
+    if (pf <= 0 || job.is != item || job.pre_tab) return;
+    const uint64_t line_bytes = n_items * (uint64_t)item;
+    uint64_t span = line_bytes;
+    if (W > 1) {
+        if (dims.empty() || dims[0].is < (int64_t)line_bytes) return;
+        span = (uint64_t)(W - 1) * (uint64_t)dims[0].is + line_bytes;
+        if (span > (uint64_t)W * line_bytes * 5 / 4) return;
+    }
+    if (span < 512 || span > (1u << 20)) return;
+    g.pf_dist = (uint32_t)pf;
+    g.pf_bytes = (uint32_t)span;
+}
+
+// line-fast tiles (lines strided, W neighbours adjacent): one prefetch per row of W items.
+// RFB200_PF_LF = distance in tiles (default 32), 0 = off.
+template <typename T>
+inline void set_prefetch_rows(TileGeom<T> &g, const LineJob &job, const std::vector<Dim> &dims, uint32_t W, int64_t item,
+                              uint64_t n_items) {
+    static const int pf = [] {
+        const char *v = getenv("RFB200_PF_LF");
+        return v ? atoi(v) : 32;
+    }();
+    // rows further apart than 64 KiB each sit on their own page: the prefetches then cost more (TLB) than they
+    // save (measured: 1024^3 c64 axis 1, rows 8 KiB apart: 58 % -> 68 %; axis 0, rows 8 MiB apart: 57 % -> 47 %)
+    const int64_t sa = job.is < 0 ? -job.is : job.is;
+    if (pf <= 0 || dims.empty() || dims[0].is != item || job.pre_tab || n_items > 65536 || sa > 65536) return;
+    g.pf_dist = (uint32_t)pf;
+    g.pf_rows = (uint32_t)n_items;
+    g.pf_bytes = (uint32_t)(W * (uint64_t)item);
+}
+
+// the same, with the memory layout of a line derived from the job's load mode (complex line of n points)
+template <typename T>
+inline void set_prefetch_by_mode(TileGeom<T> &g, const LineJob &job, const std::vector<Dim> &dims, uint32_t W) {
+    const uint64_t n_in = job.n_in ? job.n_in : job.n;
+    if (g.load_line_fast) {
+        if (job.load_mode == LD_C2C) set_prefetch_rows<T>(g, job, dims, W, sizeof(cx<T>), n_in);
+        else if (job.load_mode == LD_REAL) set_prefetch_rows<T>(g, job, dims, W, sizeof(T), n_in);
+        return;
+    }
+    switch (job.load_mode) {
+        case LD_C2C: set_prefetch<T>(g, job, dims, W, sizeof(cx<T>), n_in); break;
+        case LD_REAL: set_prefetch<T>(g, job, dims, W, sizeof(T), n_in); break;
+        case LD_HERM: set_prefetch<T>(g, job, dims, W, sizeof(cx<T>), std::min<uint64_t>(n_in, job.n / 2 + 1)); break;
+        case LD_HC: set_prefetch<T>(g, job, dims, W, sizeof(T), job.n); break;
+        default: break;
+    }
 }
 
 // pow2_launch_*.cu: returns false when the job is not one the register kernel takes

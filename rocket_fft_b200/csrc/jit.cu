@@ -353,12 +353,14 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
     if (job.prec) {
         TileGeom<double> g;
         ntiles = fill_geom<double>(g, job, dims, w, load_lf, store_lf);
+        set_prefetch_by_mode<double>(g, job, dims, w);
         g.ptw = (const double2 *)ptw;
         void *args[] = {&g};
         RFB_CUDA_CHECK(cudaLaunchKernel((const void *)ent.kern, dim3((unsigned)ntiles), dim3(threads), args, smem, s));
     } else {
         TileGeom<float> g;
         ntiles = fill_geom<float>(g, job, dims, w, load_lf, store_lf);
+        set_prefetch_by_mode<float>(g, job, dims, w);
         g.ptw = (const float2 *)ptw;
         void *args[] = {&g};
         RFB_CUDA_CHECK(cudaLaunchKernel((const void *)ent.kern, dim3((unsigned)ntiles), dim3(threads), args, smem, s));

@@ -146,6 +146,7 @@ struct Pow2Body {
         const int tid = threadIdx.x;
         const bool lf_in = g.load_line_fast != 0, lf_out = g.store_line_fast != 0;
         C v[16];
+        prefetch_later_tile<T>(g, (uint32_t)W);
 
         // ---- pass 0: global -> registers -------------------------------------------------
         {

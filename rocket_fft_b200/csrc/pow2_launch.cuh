@@ -1,6 +1,8 @@
 // Dispatch of a line job onto the instantiations of fft_pow2_kernel (one translation unit per
 // precision, see pow2_launch_f32.cu / pow2_launch_f64.cu).
 #pragma once
+#include <stdlib.h>
+
 #include "geom_fill.cuh"
 #include "pow2_kernel.cuh"
 
@@ -31,6 +33,16 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
         bool al = ((uint64_t)(uintptr_t)job.out % csz) == 0;
         for (auto &d : dims) al = al && (d.os % (int64_t)csz) == 0;
         g.flags = al ? 0 : 1;
+    }
+    if (load_lf) {
+        if (MODE == 0) set_prefetch_by_mode<T>(g, job, dims, (uint32_t)W);
+        else if (MODE == 3 || MODE == 4) set_prefetch_rows<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n);
+    } else {
+        // input items per line as they lie in memory: complex points (c2c), reals (r2c, DCT), Hermitian bins (c2r)
+        if (MODE == 0 && job.load_mode == LD_C2C) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(cx<T>), job.n_in ? job.n_in : job.n);
+        else if (MODE == 0 && job.load_mode == LD_REAL) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n_in ? job.n_in : job.n);
+        else if (MODE == 1 || MODE == 3 || MODE == 4) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n);
+        else if (MODE == 2) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(cx<T>), job.n / 2 + 1);
     }
     const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
     const size_t smem = (size_t)W * Body::PITCH * sizeof(cx<T>);

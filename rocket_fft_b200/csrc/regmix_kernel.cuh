@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fft_regmix_kernel(const TileGeo
     fdivmod(blockIdx.x, g.d_t0, rest, t0);
     fdivmod(rest, g.d_e1, c.i2, c.i1);
     c.w_first = t0 * g.W;
+    prefetch_later_tile<T>(g, g.W);
     c.wvalid = min(g.W, g.bext[0] - c.w_first);
     c.in_base = (int64_t)c.w_first * g.in_bs[0] + (int64_t)c.i1 * g.in_bs[1] + (int64_t)c.i2 * g.in_bs[2];
     c.out_base = (int64_t)c.w_first * g.out_bs[0] + (int64_t)c.i1 * g.out_bs[1] + (int64_t)c.i2 * g.out_bs[2];

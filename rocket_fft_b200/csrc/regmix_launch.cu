@@ -13,6 +13,7 @@ static void launch_regmix_inst(const LineJob &job, const std::vector<Dim> &dims,
                                bool load_lf, bool store_lf, cudaStream_t s) {
     TileGeom<T> g;
     const uint64_t ntiles = fill_geom<T>(g, job, dims, W, load_lf, store_lf);
+    set_prefetch_by_mode<T>(g, job, dims, W);
     g.ptw = (const cx<T> *)get_table(TAB_REGMIX, job.prec, job.n, pl.cap);
     const size_t smem = (size_t)W * pl.pitch * sizeof(cx<T>);
     auto kern = fft_regmix_kernel<T, ALIGNED, E, THREADS, MINB>;

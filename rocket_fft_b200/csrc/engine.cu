@@ -194,6 +194,15 @@ __global__ void blue_kernel_seq(cx<T> *b, uint32_t n, uint32_t M, const cx<T> *_
     b[m] = v;
 }
 
+// four-step order of a length n1*n2 table: dst[k1*n2 + k2] = src[k2*n1 + k1]
+template <typename T>
+__global__ void table_to_fourstep_order(cx<T> *dst, const cx<T> *__restrict__ src, uint32_t n1, uint32_t n2) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1 * n2) return;
+    const uint32_t k1 = i / n2, k2 = i % n2;
+    dst[i] = src[k2 * n1 + k1];
+}
+
 // ---------------------------------------------------------------------------------------
 // tile launch
 // ---------------------------------------------------------------------------------------
@@ -433,6 +442,7 @@ static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStrea
                                    : launch_pow2_f32(job, dims, load_lf, store_lf, s);
         if (done) return;
     }
+    if (job.conv) { set_error("internal: convolution rows need the power-of-two kernel"); throw Error(); }
     if (!job.split_out.empty()) {
         set_error("scatter output needs a power-of-two axis length between 16 and 16384 and aligned arrays");
         throw Error();
@@ -629,6 +639,101 @@ static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cuda
         const uint64_t max_lines_f = std::max<uint64_t>(1, (8ull << 30) / (M * esz));
         if (fusable && L <= max_lines_f) {
             const bool lf = !dims.empty() && (iabs64(dims[0].is) < iabs64(job.is) || iabs64(dims[0].os) < iabs64(job.os));
+            uint64_t n1 = 0, n2 = 0;
+            if (!lf && M > (1ull << 14) && job.is == (int64_t)esz && job.os == (int64_t)esz && choose_split(M, job.prec, n1, n2)) {
+                // Long contiguous lines: M = n1*n2 needs two launches per transform anyway.  A convolution does not
+                // need its spectrum in natural order, so the forward transform leaves it in four-step order
+                // ([k1][k2], bin k2*n1 + k1) and the backward transform consumes that order: of the four launches
+                // only the two n1-point column passes touch strided memory, the two n2-point row passes run in
+                // place on contiguous lines, and one work buffer suffices.
+                //   A : n1-point DFTs down the columns of x (chirp and zero padding on the load), times w_M^(j0 k1)
+                //   B : n2-point DFTs along the rows, times B^ (stored in four-step order)
+                //   B': n2-point backward DFTs along the rows, times conj w_M^(j0 k1)
+                //   A': n1-point backward DFTs down the columns -> natural order, chirp / fct / truncation on the store
+                // (B and B' are one kernel, MODE 5 of the power-of-two kernel: three passes over HBM in total)
+                const void *bhat_t;
+                {
+                    std::lock_guard<std::mutex> lk(g_blue_mu);
+                    bool created = false;
+                    void *w = nullptr;
+                    bhat_t = get_table(TAB_CHIRP_FFT_T, job.prec, n, M, &created, &w);
+                    if (created) {
+                        dim3 grid((unsigned)((M + 255) / 256));
+                        if (job.prec) table_to_fourstep_order<double><<<grid, 256, 0, s>>>((double2 *)w, (const double2 *)bhat, (uint32_t)n1, (uint32_t)n2);
+                        else table_to_fourstep_order<float><<<grid, 256, 0, s>>>((float2 *)w, (const float2 *)bhat, (uint32_t)n1, (uint32_t)n2);
+                        RFB_AFTER_LAUNCH();
+                        RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+                    }
+                }
+                std::vector<int64_t> st(dims.size());
+                int64_t acc2 = (int64_t)(M * esz);
+                for (size_t i = 0; i < dims.size(); ++i) { st[i] = acc2; acc2 *= dims[i].n; }
+                Scratch s1(L * M * esz, s);
+                const int64_t e = (int64_t)esz, row = (int64_t)n2 * e;
+                LineJob A;
+                A.prec = job.prec;
+                A.n = n1;
+                A.is = row;
+                A.os = row;
+                for (size_t i = 0; i < dims.size(); ++i) A.batch.push_back(Dim{dims[i].n, dims[i].is, st[i], false});
+                A.batch.push_back(Dim{(int64_t)n2, e, e, true});
+                A.in = job.in;
+                A.out = (char *)s1.p;
+                A.twN = M;
+                A.pre_tab = chirp;
+                A.pre_bound = n;
+                A.pre_swap = job.backward;
+                A.g_mul = n2;
+                run_lines(A, s);
+                LineJob B;
+                B.prec = job.prec;
+                B.n = n2;
+                B.is = B.os = e;
+                for (size_t i = 0; i < dims.size(); ++i) B.batch.push_back(Dim{dims[i].n, st[i], st[i], false});
+                B.batch.push_back(Dim{(int64_t)n1, row, row, true});
+                B.in = (const char *)s1.p;
+                B.out = (char *)s1.p;
+                B.post_tab = bhat_t;
+                B.post_bound = M;
+                B.g_mul = 1;
+                B.c_mul = n2;
+                // B and B' work on the same rows: one kernel does both without leaving the SM when it can
+                LineJob Cv = B;
+                Cv.conv = true;
+                Cv.pre_tab = bhat_t;
+                Cv.pre_bound = M;
+                Cv.post_tab = nullptr;
+                Cv.post_bound = 0;
+                Cv.twN = M;
+                static const bool use_conv = env_int("RFB200_NO_CONV_ROW", 0) == 0;
+                if (!(use_conv && run_lines_pow2(Cv, s))) {
+                    run_lines(B, s);
+                    LineJob Bi = B;
+                    Bi.post_tab = nullptr;
+                    Bi.post_bound = 0;
+                    Bi.c_mul = 1;
+                    Bi.backward = true;
+                    Bi.twN = M;
+                    run_lines(Bi, s);
+                }
+                LineJob Ai;
+                Ai.prec = job.prec;
+                Ai.n = n1;
+                Ai.is = row;
+                Ai.os = row;
+                for (size_t i = 0; i < dims.size(); ++i) Ai.batch.push_back(Dim{dims[i].n, st[i], dims[i].os, false});
+                Ai.batch.push_back(Dim{(int64_t)n2, e, e, true});
+                Ai.in = (const char *)s1.p;
+                Ai.out = job.out;
+                Ai.backward = true;
+                Ai.fct = job.fct;
+                Ai.post_tab = chirp;
+                Ai.post_bound = n;
+                Ai.post_swap = job.backward;
+                Ai.g_mul = n2;
+                run_lines(Ai, s);
+                return;
+            }
             std::vector<int64_t> sstr(dims.size());
             int64_t s_axis, acc;
             if (lf) {

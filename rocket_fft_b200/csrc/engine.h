@@ -35,13 +35,16 @@ struct LineJob {
     // the usual offset arithmetic with the full index k applies); empty: everything goes to `out`
     std::vector<char *> split_out;
     uint64_t split_blk = 0;
-    // element-wise factors fused into the load / store (Bluestein): with g = e * g_mul + c, c the
+    // element-wise factors fused into the load / store (Bluestein): with g = e * g_mul + c * c_mul, c the
     // coordinate along the batch dim flagged `tw` (0 if none),
     //   load : x[e] * pre_tab[g] if g < pre_bound else 0          (pre_swap: swap re/im of x first)
     //   store: bin skipped if g >= post_bound, else value * post_tab[g]   (post_swap: swap re/im last)
     const void *pre_tab = nullptr, *post_tab = nullptr;
-    uint64_t pre_bound = 0, post_bound = 0, g_mul = 1;
+    uint64_t pre_bound = 0, post_bound = 0, g_mul = 1, c_mul = 1;
     bool pre_swap = false, post_swap = false;
+    // circular-convolution line (power-of-two kernel only, contiguous lines): forward transform, times pre_tab[g]
+    // with g indexed by the BIN, backward transform; twN / fct apply to the final store
+    bool conv = false;
 };
 
 void run_lines(const LineJob &job, cudaStream_t stream);

@@ -57,6 +57,7 @@ inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<
     g.in = job.in;
     g.out = job.out;
     g.g_mul = (uint32_t)job.g_mul;
+    g.c_mul = (uint32_t)job.c_mul;
     g.pre_tab = (const cx<T> *)job.pre_tab;
     g.post_tab = (const cx<T> *)job.post_tab;
     g.pre_bound = (uint32_t)job.pre_bound;

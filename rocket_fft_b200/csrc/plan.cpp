@@ -259,7 +259,8 @@ const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool
         case TAB_SPLIT_A: count = (n + param - 1) / param + 1; break;
         case TAB_SPLIT_B: count = param; break;
         case TAB_CHIRP: count = n; break;
-        case TAB_CHIRP_FFT: count = param; break;
+        case TAB_CHIRP_FFT:
+        case TAB_CHIRP_FFT_T: count = param; break;
         case TAB_QUARTER: count = n + 1; break;
         case TAB_STOCKHAM:
         case TAB_REGMIX:
@@ -278,7 +279,7 @@ const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool
             fill_stockham(h, n, kind == TAB_TILE ? 1 : (kind == TAB_REGMIX ? 2 : 0), param);
             RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
-    } else if (kind != TAB_CHIRP_FFT) {
+    } else if (kind != TAB_CHIRP_FFT && kind != TAB_CHIRP_FFT_T) {
         if (prec) {
             std::vector<double> h;
             fill(h, kind, n, param, count);

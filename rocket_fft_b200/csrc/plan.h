@@ -33,6 +33,7 @@ enum TableKind : int {
     TAB_SPLIT_B = 2,   // exp(-2 pi i t / n), t in [0, S)
     TAB_CHIRP = 3,     // exp(-i pi t^2 / n), t in [0, n)
     TAB_CHIRP_FFT = 4, // forward DFT_M of the wrapped conjugate chirp, divided by M  (param = M)
+    TAB_CHIRP_FFT_T = 9, // the same in four-step order: entry k1*n2 + k2 holds bin k2*n1 + k1  (param = M)
     TAB_QUARTER = 5,   // exp(-2 pi i t / (4 n)), t in [0, n]   (DCT/DST and real pre/post factors)
     TAB_REGMIX = 8,    // pass-major twiddles for regmix_schedule(n, param)  (param = radix cap)
     TAB_TILE = 7,      // pass-major twiddles of the generic tile kernel for radix_schedule(n, 64)

@@ -158,7 +158,7 @@ struct Pow2Body {
             // All 16 loads are issued back to back with nothing depending on them in between
             // (memory-level parallelism: 16 independent requests per thread in flight).
             const bool packed_vec = (MODE == 1) && g.in_sa == (int64_t)sizeof(T);
-            const bool plain = (MODE == 0) && g.load_mode == LD_C2C && g.n_in == (uint32_t)N;
+            const bool plain = (MODE == 0 || MODE == 5) && g.load_mode == LD_C2C && g.n_in == (uint32_t)N;
             if (MODE == 2) {
                 // Packed inverse real transform: the N+1 Hermitian bins X are folded into the N-point
                 // complex spectrum  Z[e] = (X[e] + conj X[N-e]) + i w^e (X[e] - conj X[N-e]),
@@ -256,8 +256,8 @@ struct Pow2Body {
                 }
             } else if (MODE == 0 && g.pre_tab != nullptr) {
                 // zero-padded load with a fused element-wise factor (Bluestein's chirp): global index
-                // gi = e * g_mul + c decides both the padding and the table entry
-                const uint32_t c = g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2));
+                // gi = e * g_mul + c * c_mul decides both the padding and the table entry
+                const uint32_t c = (g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2))) * g.c_mul;
                 const int64_t sa = g.in_sa;
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
@@ -349,6 +349,42 @@ struct Pow2Body {
         constexpr int RL = PL::radix(PL::NPASS - 1), NBL = 16 / RL;
         int w, t;
         map(PL::NPASS > 1 ? lf_out : lf_in, tid, w, t);
+        if constexpr (MODE == 5) {
+            // Circular-convolution row (Bluestein's middle): the spectrum just computed is multiplied by
+            // pre_tab[bin * g_mul + c * c_mul], and transformed back without leaving the SM.  One trip through shared
+            // memory turns the output distribution of the last pass (bins t + q N/RL) into the input distribution
+            // of pass 0 (elements t + m ido).  The backward transform is swap . forward . swap; the final swap
+            // is the store path's.
+            const uint32_t cc = (g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2))) * g.c_mul;
+            const bool wok5 = (W == 1) ? true : (w < wvalid);
+#pragma unroll
+            for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const uint32_t k = (uint32_t)(t + j * TPL + q * (N / RL));
+                    C val = v[j * RL + q];
+                    if (wok5) val = cmul(val, __ldg(g.pre_tab + (k * g.g_mul + cc)));
+                    v[j * RL + q] = cswap(val);
+                }
+            if (!first) __syncthreads();
+            C *sl = buf + w * PITCH;
+#pragma unroll
+            for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                for (int q = 0; q < RL; ++q) sl[t + j * TPL + q * (N / RL)] = v[j * RL + q];
+            __syncthreads();
+            {
+                constexpr int R0 = PL::radix(0), NB0 = 16 / R0, ido0 = PL::ido(0);
+#pragma unroll
+                for (int j = 0; j < NB0; ++j)
+#pragma unroll
+                    for (int m = 0; m < R0; ++m) v[j * R0 + m] = sl[t + j * TPL + m * ido0];
+            }
+            compute<0>(v, t, stw);
+            if constexpr (PL::NPASS > 1) { exchange<1>(v, buf, tid, false, false, false); compute<1>(v, t, stw); }
+            if constexpr (PL::NPASS > 2) { exchange<2>(v, buf, tid, false, false, false); compute<2>(v, t, stw); }
+            if constexpr (PL::NPASS > 3) { exchange<3>(v, buf, tid, false, false, false); compute<3>(v, t, stw); }
+        }
         if (MODE == 2 || MODE == 4) {
             // bins hold swap(x[2k] + i x[2k+1]); deliver the two reals
             if (w >= wvalid) return;
@@ -379,13 +415,13 @@ struct Pow2Body {
                 }
             return;
         }
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 5) {
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
             if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C) && g.split_blk == 0 &&
                 g.post_tab == nullptr) {
                 const T f = g.fct;
-                const bool bw = g.backward != 0;
+                const bool bw = (MODE == 5) || g.backward != 0;
                 C *p = reinterpret_cast<C *>(line) + t;
 #pragma unroll
                 for (int j = 0; j < NBL; ++j)
@@ -401,7 +437,7 @@ struct Pow2Body {
                 // strided output, optionally with the four-step factor exp(-2 pi i c k / bigN):
                 // exact two-level table look-ups for every 4th bin, three recurrence steps between
                 const T f = g.fct;
-                const bool bw = g.backward != 0;
+                const bool bw = (MODE == 5) || g.backward != 0;
                 const bool tw = g.tw_dim >= 0;
                 const uint32_t c = tw ? ((g.tw_dim == 0) ? (w_first + w) : (g.tw_dim == 1 ? i1 : i2)) : 0u;
                 auto lookup = [&](uint32_t x) {
@@ -429,7 +465,7 @@ struct Pow2Body {
                         if (bw) val = cswap(val);
                         if (g.post_tab != nullptr) {
                             // fused element-wise factor / truncation on the way out (Bluestein)
-                            const uint32_t cc = g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2));
+                            const uint32_t cc = (g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2))) * g.c_mul;
                             const uint32_t bin = (uint32_t)(t + j * TPL + q * (N / RL)) * g.g_mul + cc;
                             if (bin >= g.post_bound) { pq += step_q; continue; }
                             val = cmul(val, __ldg(g.post_tab + bin));

@@ -21,9 +21,9 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
     using Body = Pow2Body<T, LOGN, W, MODE>;
     TileGeom<T> g;
     LineJob j2 = job;
-    if (MODE != 0) j2.n = job.n / 2;  // geometry in complex points
+    if (MODE != 0 && MODE != 5) j2.n = job.n / 2;  // geometry in complex points
     const uint64_t ntiles = fill_geom<T>(g, j2, dims, (uint32_t)W, load_lf, store_lf);
-    if (MODE != 0) {
+    if (MODE != 0 && MODE != 5) {
         g.n_out = (uint32_t)(job.n / 2 + 1);
         g.twA = (const cx<T> *)get_table(TAB_LINE, job.prec, job.n, 0);
     }
@@ -40,7 +40,11 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
         else if (MODE == 3 || MODE == 4) set_prefetch_rows<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n);
     } else {
         // input items per line as they lie in memory: complex points (c2c), reals (r2c, DCT), Hermitian bins (c2r)
-        if (MODE == 0 && job.load_mode == LD_C2C) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(cx<T>), job.n_in ? job.n_in : job.n);
+        if (MODE == 5) {
+            LineJob jp = job;
+            jp.pre_tab = nullptr;  // here the table multiplies the spectrum, every input element is read
+            set_prefetch<T>(g, jp, dims, (uint32_t)W, sizeof(cx<T>), job.n);
+        } else if (MODE == 0 && job.load_mode == LD_C2C) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(cx<T>), job.n_in ? job.n_in : job.n);
         else if (MODE == 0 && job.load_mode == LD_REAL) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n_in ? job.n_in : job.n);
         else if (MODE == 1 || MODE == 3 || MODE == 4) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n);
         else if (MODE == 2) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(cx<T>), job.n / 2 + 1);
@@ -66,6 +70,13 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     constexpr bool dbl = sizeof(T) == 8;
     constexpr int WE = p2_we(LOGN), WL = p2_wl(LOGN, dbl);
     const bool lf = load_lf || store_lf;
+    if (mode == 5) {
+        if constexpr (LOGN >= 8 && LOGN <= 11) {
+            if (lf) return false;
+            launch_pow2_inst<T, LOGN, WE, 5>(job, dims, false, false, s);
+            return true;
+        } else return false;
+    }
     if (mode == 1 || mode == 2) {
         if (lf) return false;
         if (mode == 1) launch_pow2_inst<T, LOGN, WE, 1>(job, dims, load_lf, store_lf, s);
@@ -104,6 +115,12 @@ bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load
     int mode = 0;
     uint64_t n = job.n;
     const bool plain_in = job.n_in == 0 || job.n_in == job.n;
+    if (job.conv) {
+        if (job.load_mode != LD_C2C || job.store_mode != ST_C2C || !job.pre_tab || job.post_tab || !plain_in || load_lf ||
+            store_lf || !job.split_out.empty() || job.flags)
+            return false;
+        mode = 5;
+    } else
     if (job.load_mode == LD_REAL && job.store_mode == ST_HALF && job.flags == 0 && plain_in && job.twN == 0 &&
         (n % 2 == 0) && !load_lf && !store_lf && n >= 32) {
         // the packed load reads two reals as one complex value: needs complex alignment
@@ -123,7 +140,7 @@ bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load
         n /= 2;
     } else if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
     if (!job.split_out.empty() && (mode != 0 || job.store_mode != ST_C2C)) return false;
-    if ((job.pre_tab || job.post_tab) && (mode != 0 || job.store_mode != ST_C2C || job.load_mode != LD_C2C)) return false;
+    if ((job.pre_tab || job.post_tab) && ((mode != 0 && mode != 5) || job.store_mode != ST_C2C || job.load_mode != LD_C2C)) return false;
     if (n < 16 || (n & (n - 1))) return false;
     int logn = 0;
     while ((1ull << logn) < n) ++logn;

@@ -66,8 +66,8 @@ struct TileGeom {
     FastDiv d_split;
     char *split_base[16];
     // fused element-wise factors (power-of-two kernel only), see LineJob
-    int c_dim;           // batch dim whose coordinate enters g = e * g_mul + c (-1: c = 0)
-    uint32_t g_mul, pre_bound, post_bound;
+    int c_dim;           // batch dim whose coordinate enters g = e * g_mul + c * c_mul (-1: c = 0)
+    uint32_t g_mul, c_mul, pre_bound, post_bound;
     const cx<T> *pre_tab, *post_tab;
     int pre_swap, post_swap;
 };

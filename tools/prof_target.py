@@ -36,6 +36,14 @@ elif name == "cfg4a":
     x = torch.randn(4096, 15015, dtype=torch.complex64, device=dev)
     y = torch.empty_like(x)
     fn = lambda: R.c2c(x, y, [1], True, 1.0)
+elif name == "cfg4b":
+    x = torch.randn(256, 1000003, dtype=torch.complex64, device=dev)
+    y = torch.empty_like(x)
+    fn = lambda: R.c2c(x, y, [1], True, 1.0)
+elif name == "cfg5":
+    x = torch.randn(2048, 2048, 64, dtype=torch.float64, device=dev)
+    y = torch.empty_like(x)
+    fn = lambda: R.dct(x, y, [0, 1], 2, 1.0, False)
 else:
     raise SystemExit("unknown workload")
 for _ in range(reps):

@@ -640,7 +640,15 @@ static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cuda
         if (fusable && L <= max_lines_f) {
             const bool lf = !dims.empty() && (iabs64(dims[0].is) < iabs64(job.is) || iabs64(dims[0].os) < iabs64(job.os));
             uint64_t n1 = 0, n2 = 0;
-            if (!lf && M > (1ull << 14) && job.is == (int64_t)esz && job.os == (int64_t)esz && choose_split(M, job.prec, n1, n2)) {
+            if (!lf && M > (1ull << 14) && job.is == (int64_t)esz && job.os == (int64_t)esz) {
+                // rows of n2 = 4096 points (the contiguous kernel's sweet spot), columns of n1 = M / n2 >= 16 points:
+                // short columns mean wide tiles (many neighbouring columns per CTA) for the strided passes
+                static const int log_n2 = env_int("RFB200_BLUE_LOGN2", 12);
+                int l2 = std::min(std::max(log_n2, 8), 13);
+                while (logM - l2 < 4) --l2;
+                while (logM - l2 > 11) ++l2;
+                n2 = 1ull << l2;
+                n1 = M >> l2;
                 // Long contiguous lines: M = n1*n2 needs two launches per transform anyway.  A convolution does not
                 // need its spectrum in natural order, so the forward transform leaves it in four-step order
                 // ([k1][k2], bin k2*n1 + k1) and the backward transform consumes that order: of the four launches

@@ -71,7 +71,7 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     constexpr int WE = p2_we(LOGN), WL = p2_wl(LOGN, dbl);
     const bool lf = load_lf || store_lf;
     if (mode == 5) {
-        if constexpr (LOGN >= 8 && LOGN <= 11) {
+        if constexpr (LOGN >= 8 && LOGN <= 13) {
             if (lf) return false;
             launch_pow2_inst<T, LOGN, WE, 5>(job, dims, false, false, s);
             return true;

@@ -11,7 +11,8 @@ namespace rfb {
 // lines per CTA: element-fast tiles aim at 256 threads, line-fast tiles at >= 128-byte rows
 constexpr int p2_we(int logn) { return logn <= 10 ? (256 >> (logn - 4)) : (logn == 11 ? 2 : 1); }
 // (measured on B200: 1024-point float lines 8 MiB apart: W=8 -> 2.9 TB/s, W=16 -> 3.7 TB/s;
-//  128-point float lines of the four-step column passes: W=32 -> 0.82 ms, W=64 -> 0.88 ms per 16384^2 image)
+//  128-point float lines of the four-step column passes: W=32 -> 0.82 ms, W=64 -> 0.88 ms per 16384^2 image;
+//  1024-point double lines of the fused DCT, 64 contiguous doubles per row: W=8 -> 2.64 ms, W=4 -> 3.86 ms)
 constexpr int p2_wl(int logn, bool dbl) {
     return logn <= 8 ? p2_we(logn) : (logn == 9 ? 16 : (logn == 10 ? (dbl ? 8 : 16) : (logn == 11 ? (dbl ? 4 : 8) : 0)));
 }

@@ -88,8 +88,9 @@ struct SpecKey {
     int dev, prec;
     uint64_t n;
     uint32_t tpl, w;
+    int kmode;
     bool operator<(const SpecKey &o) const {
-        return std::tie(dev, prec, n, tpl, w) < std::tie(o.dev, o.prec, o.n, o.tpl, o.w);
+        return std::tie(dev, prec, n, tpl, w, kmode) < std::tie(o.dev, o.prec, o.n, o.tpl, o.w, o.kmode);
     }
 };
 struct SpecEntry {
@@ -207,19 +208,19 @@ bool nvrtc_build(const std::string &src, const std::string &name, uint64_t n, st
     return ok;
 }
 
-bool compile_spec(int prec, uint64_t n, uint32_t tpl, uint32_t w, uint32_t minb, const std::vector<uint32_t> &sched,
-                  SpecEntry &out) {
+bool compile_spec(int prec, int kmode, uint64_t n, uint32_t tpl, uint32_t w, uint32_t minb,
+                  const std::vector<uint32_t> &sched, SpecEntry &out) {
     const char *T = prec ? "double" : "float";
     const bool verbose = getenv("RFB200_JIT_VERBOSE") != nullptr;
     std::string rad;
     for (size_t i = 0; i < sched.size(); ++i) rad += (i ? ", " : "") + std::to_string(sched[i]);
-    const std::string name = std::string("rfb::fft_spec_kernel<") + T + ", rfb::PJ, true>";
+    const std::string name = std::string("rfb::fft_spec_kernel<") + T + ", rfb::PJ, true, " + std::to_string(kmode) + ">";
     std::string lname;
     std::vector<char> cubin;
     const std::string dir = cache_dir();
     char key[64];
     snprintf(key, sizeof(key), "%016llx",
-             (unsigned long long)fnv1a(std::string(T) + "|" + std::to_string(n) + "|" + std::to_string(tpl) + "|" +
+             (unsigned long long)fnv1a(std::string(T) + "|" + std::to_string(kmode) + "|" + std::to_string(n) + "|" + std::to_string(tpl) + "|" +
                                        std::to_string(w) + "|" + std::to_string(minb) + "|" + rad + "|" + header_stamp()));
     const std::string path = dir.empty() ? std::string() : dir + "/spec_" + key + ".cubin";
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -237,14 +238,14 @@ bool compile_spec(int prec, uint64_t n, uint32_t tpl, uint32_t w, uint32_t minb,
                      "    static constexpr int N = %llu, TPL = %u, W = %u, NPASS = %zu, MINB = %u;\n"
                      "    __host__ __device__ static constexpr int radix(int s) { constexpr int r[%zu] = {%s}; return r[s]; }\n"
                      "};\n"
-                     "template __global__ void fft_spec_kernel<%s, PJ, true>(const TileGeom<%s>);\n"
+                     "template __global__ void fft_spec_kernel<%s, PJ, true, %d>(const TileGeom<%s>);\n"
                      "}\n",
-                     (unsigned long long)n, tpl, w, sched.size(), mb, sched.size(), rad.c_str(), T, T);
+                     (unsigned long long)n, tpl, w, sched.size(), mb, sched.size(), rad.c_str(), T, kmode, T);
             long spill = 0;
             if (!nvrtc_build(src, name, n, lname, cubin, &spill)) return false;
             if (verbose)
-                fprintf(stderr, "rocketfft_b200: jit n=%llu %s tpl=%u w=%u minb=%u [%s] spill=%ld B\n",
-                        (unsigned long long)n, T, tpl, w, mb, rad.c_str(), spill);
+                fprintf(stderr, "rocketfft_b200: jit n=%llu %s mode=%d tpl=%u w=%u minb=%u [%s] spill=%ld B\n",
+                        (unsigned long long)n, T, kmode, tpl, w, mb, rad.c_str(), spill);
             if (spill <= 64 || mb <= 1) {
                 if (!path.empty()) cache_write(path, lname, cubin);
                 have = true;
@@ -274,7 +275,15 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
         return v ? atoi(v) : 1;  // 0: off, 1: for large batches, 2: always
     }();
     if (mode == 0 || !aligned || dims.size() > (size_t)MAXB) return false;
-    const uint64_t n = job.n;
+    // packed real transform (kernel MODE 1): contiguous even-length real line -> half spectrum through an n/2-point
+    // complex transform; the two reals of a point are read as one complex value, which needs complex alignment
+    const int64_t rsz = job.prec ? 8 : 4;
+    bool packed = job.load_mode == LD_REAL && job.store_mode == ST_HALF && job.flags == 0 && job.twN == 0 && job.n % 2 == 0 &&
+                  job.n >= 12 && !load_lf && !store_lf && job.is == rsz && ((uintptr_t)job.in % (2 * rsz)) == 0;
+    for (auto &d : dims) packed = packed && (d.is % (2 * rsz)) == 0;
+    if (packed && regmix_schedule(job.n / 2, job.prec ? 8 : 16).empty() && regmix_schedule(job.n / 2, 16).empty()) packed = false;
+    const int kmode = packed ? 1 : 0;
+    const uint64_t n = packed ? job.n / 2 : job.n;
     if (n < 6 || n > 32768 || (n & (n - 1)) == 0) return false;
     if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
     if (!job.split_out.empty() || job.pre_tab || job.post_tab) return false;
@@ -330,13 +339,13 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
     SpecEntry ent;
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        SpecKey key{dev, job.prec, n, tpl, w};
+        SpecKey key{dev, job.prec, n, tpl, w, kmode};
         auto it = g_cache.find(key);
         if (it == g_cache.end()) {
             SpecEntry e;
             e.smem = smem;
             e.cap = cap;
-            if (compile_spec(job.prec, n, tpl, w, minb, sched, e) && e.kern) {
+            if (compile_spec(job.prec, kmode, n, tpl, w, minb, sched, e) && e.kern) {
                 if (cudaFuncSetAttribute((const void *)e.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
                     cudaSuccess) {
                     cudaGetLastError();
@@ -349,22 +358,23 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
     }
     if (!ent.kern) return false;
     const void *ptw = get_table(TAB_REGMIX, job.prec, n, cap);
-    uint64_t ntiles;
-    if (job.prec) {
-        TileGeom<double> g;
-        ntiles = fill_geom<double>(g, job, dims, w, load_lf, store_lf);
-        set_prefetch_by_mode<double>(g, job, dims, w);
-        g.ptw = (const double2 *)ptw;
+    auto launch = [&](auto tag) {
+        using T = decltype(tag);
+        TileGeom<T> g;
+        LineJob j2 = job;
+        if (packed) j2.n = n;  // geometry in complex points
+        const uint64_t ntiles = fill_geom<T>(g, j2, dims, w, load_lf, store_lf);
+        set_prefetch_by_mode<T>(g, job, dims, w);
+        if (packed) {
+            g.n_in = (uint32_t)(job.n_in ? job.n_in : job.n);  // real samples present
+            g.twA = (const cx<T> *)get_table(TAB_LINE, job.prec, job.n, 0);
+        }
+        g.ptw = (const cx<T> *)ptw;
         void *args[] = {&g};
         RFB_CUDA_CHECK(cudaLaunchKernel((const void *)ent.kern, dim3((unsigned)ntiles), dim3(threads), args, smem, s));
-    } else {
-        TileGeom<float> g;
-        ntiles = fill_geom<float>(g, job, dims, w, load_lf, store_lf);
-        set_prefetch_by_mode<float>(g, job, dims, w);
-        g.ptw = (const float2 *)ptw;
-        void *args[] = {&g};
-        RFB_CUDA_CHECK(cudaLaunchKernel((const void *)ent.kern, dim3((unsigned)ntiles), dim3(threads), args, smem, s));
-    }
+    };
+    if (job.prec) launch(double());
+    else launch(float());
     count_launch();
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;

@@ -157,7 +157,8 @@ struct Pow2Body {
             const char *line = g.in + in_base + (int64_t)w * g.in_bs[0];
             // All 16 loads are issued back to back with nothing depending on them in between
             // (memory-level parallelism: 16 independent requests per thread in flight).
-            const bool packed_vec = (MODE == 1) && g.in_sa == (int64_t)sizeof(T);
+            // MODE 1: n_in counts REAL samples present (2N when the line is not zero-padded)
+            const bool packed_vec = (MODE == 1) && g.in_sa == (int64_t)sizeof(T) && g.n_in == 2u * (uint32_t)N;
             const bool plain = (MODE == 0 || MODE == 5) && g.load_mode == LD_C2C && g.n_in == (uint32_t)N;
             if (MODE == 2) {
                 // Packed inverse real transform: the N+1 Hermitian bins X are folded into the N-point
@@ -311,8 +312,8 @@ struct Pow2Body {
                         C val = mk<T>(T(0), T(0));
                         if (wok) {
                             if (MODE == 1) {
-                                val.x = *reinterpret_cast<const T *>(line + (int64_t)(2 * e) * g.in_sa);
-                                val.y = *reinterpret_cast<const T *>(line + (int64_t)(2 * e + 1) * g.in_sa);
+                                if (2 * e < g.n_in) val.x = *reinterpret_cast<const T *>(line + (int64_t)(2 * e) * g.in_sa);
+                                if (2 * e + 1 < g.n_in) val.y = *reinterpret_cast<const T *>(line + (int64_t)(2 * e + 1) * g.in_sa);
                             } else val = load_value<T, true>(g.load_mode, g.flags, line, g.in_sa, e, (uint32_t)N, g.n_in);
                         }
                         v[j * R + m] = val;

@@ -28,6 +28,7 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
         g.n_out = (uint32_t)(job.n / 2 + 1);
         g.twA = (const cx<T> *)get_table(TAB_LINE, job.prec, job.n, 0);
     }
+    if (MODE == 1) g.n_in = (uint32_t)(job.n_in ? job.n_in : job.n);  // real samples present
     if (MODE == 3 || MODE == 4) g.twB = (const cx<T> *)get_table(TAB_QUARTER, job.prec, job.n, 0);
     if (MODE == 2) {
         // the two reals of an output point are stored as one complex value when aligned
@@ -47,7 +48,8 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
             set_prefetch<T>(g, jp, dims, (uint32_t)W, sizeof(cx<T>), job.n);
         } else if (MODE == 0 && job.load_mode == LD_C2C) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(cx<T>), job.n_in ? job.n_in : job.n);
         else if (MODE == 0 && job.load_mode == LD_REAL) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n_in ? job.n_in : job.n);
-        else if (MODE == 1 || MODE == 3 || MODE == 4) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n);
+        else if (MODE == 1) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n_in ? job.n_in : job.n);
+        else if (MODE == 3 || MODE == 4) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n);
         else if (MODE == 2) set_prefetch<T>(g, job, dims, (uint32_t)W, sizeof(cx<T>), job.n / 2 + 1);
     }
     const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
@@ -122,7 +124,7 @@ bool launch_pow2_any(const LineJob &job, const std::vector<Dim> &dims, bool load
             return false;
         mode = 5;
     } else
-    if (job.load_mode == LD_REAL && job.store_mode == ST_HALF && job.flags == 0 && plain_in && job.twN == 0 &&
+    if (job.load_mode == LD_REAL && job.store_mode == ST_HALF && job.flags == 0 && job.twN == 0 &&
         (n % 2 == 0) && !load_lf && !store_lf && n >= 32) {
         // the packed load reads two reals as one complex value: needs complex alignment
         const uint64_t csz = 2 * sizeof(T);

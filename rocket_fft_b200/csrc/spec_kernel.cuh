@@ -4,7 +4,9 @@
 // arbitrary smooth lengths).  Instantiated at run time through NVRTC (jit.cu) for the length at hand --
 // the same source a build-time instantiation would use -- with regmix_kernel.cuh as the fallback.
 //
-// P must provide:  N, TPL, W, NPASS (static constexpr int) and static constexpr int radix(int s).
+// P must provide:  N, TPL, W, NPASS, MINB (static constexpr int) and static constexpr int radix(int s).
+// MODE 0: complex line job (all load / store modes of line_io.cuh);  MODE 1: packed real -> half spectrum of a
+// contiguous even-length real line (N = half the real length), the structure of MODE 1 in pow2_kernel.cuh.
 #pragma once
 #include "common.cuh"
 #include "line_io.cuh"
@@ -30,7 +32,7 @@ struct SpecInfo {
     __host__ __device__ static constexpr int J(int s) { return (P::N / P::radix(s) + P::TPL - 1) / P::TPL; }
 };
 
-template <typename T, typename P, int S, bool ALIGNED>
+template <typename T, typename P, int S, bool ALIGNED, int MODE>
 struct SpecPass {
     using C = cx<T>;
     using I = SpecInfo<P>;
@@ -51,8 +53,25 @@ struct SpecPass {
         const C *tws = g.ptw + I::twoff(S);
         if constexpr (FIRST) {
             const char *line = g.in + in_base + (int64_t)w * g.in_bs[0];
-            const bool plain = g.load_mode == LD_C2C && g.n_in == (uint32_t)N;
-            if (plain && g.in_sa == (int64_t)sizeof(C)) {
+            const bool plain = MODE == 0 && g.load_mode == LD_C2C && g.n_in == (uint32_t)N;
+            if (MODE == 1) {
+                // packed real transform: the contiguous real line (n_in samples present, the rest zero padding) is
+                // read as N complex points x[2e] + i x[2e+1]; the host guarantees complex alignment
+                const C *p = reinterpret_cast<const C *>(line) + t;
+                const bool full = g.n_in == 2u * (uint32_t)N;
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const int e = t + j * TPL + m * IDO;
+                        C val = mk<T>(T(0), T(0));
+                        if (wok && (EXACT || t + j * TPL < NB)) {
+                            if (full || 2u * (uint32_t)e + 1u < g.n_in) val = __ldcs(p + j * TPL + m * IDO);
+                            else if (2u * (uint32_t)e < g.n_in) val.x = *reinterpret_cast<const T *>(line + (int64_t)(2 * e) * sizeof(T));
+                        }
+                        v[j * R + m] = val;
+                    }
+            } else if (plain && g.in_sa == (int64_t)sizeof(C)) {
                 const C *p = reinterpret_cast<const C *>(line) + t;
 #pragma unroll
                 for (int j = 0; j < J; ++j)
@@ -76,7 +95,7 @@ struct SpecPass {
                         v[j * R + m] = val;
                     }
             }
-            if (g.backward) {
+            if (MODE == 0 && g.backward) {
 #pragma unroll
                 for (int q = 0; q < J * R; ++q) v[q] = cswap(v[q]);
             }
@@ -104,7 +123,45 @@ struct SpecPass {
                 }
             }
         }
-        if constexpr (LAST) {
+        if constexpr (LAST && MODE == 1) {
+            // Hermitian unpack: Z = DFT_N(x[2j] + i x[2j+1]) -> X[k] = E + O, X[N-k] = conj(E - O) with
+            // E = (Z[k] + conj Z[N-k])/2, O = -i w^k (Z[k] - conj Z[N-k])/2, w = exp(-2 pi i/(2N)), through one more trip
+            // over shared memory (natural order)
+            if (P::NPASS > 1) __syncthreads();
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int b = t + j * TPL;
+                if (EXACT || b < NB) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) sl[b + q * NB] = v[j * R + q];
+                }
+            }
+            __syncthreads();
+            if (!wok) return;
+            char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
+            const T half = T(0.5) * g.fct;
+            const bool conj_out = g.backward != 0;
+            const bool contig_out = g.out_sa == (int64_t)sizeof(C);
+            for (int k = t; k <= N / 2; k += TPL) {
+                const C a = sl[k];
+                const C bz = sl[k ? N - k : 0];
+                const C bb = mk<T>(bz.x, -bz.y);
+                const C e = mk<T>((a.x + bb.x) * half, (a.y + bb.y) * half);
+                const C d = mk<T>((a.x - bb.x) * half, (a.y - bb.y) * half);
+                const C wd = cmul(__ldg(g.twA + k), d);
+                const C o = mk<T>(wd.y, -wd.x);  // -i w^k d
+                C x0 = mk<T>(e.x + o.x, e.y + o.y);
+                C x1 = mk<T>(e.x - o.x, -(e.y - o.y));
+                if (conj_out) { x0.y = -x0.y; x1.y = -x1.y; }
+                if (contig_out) {
+                    __stcs(reinterpret_cast<C *>(line) + k, x0);
+                    __stcs(reinterpret_cast<C *>(line) + (N - k), x1);
+                } else {
+                    st_cx<T, ALIGNED>(line + (int64_t)k * g.out_sa, x0);
+                    st_cx<T, ALIGNED>(line + (int64_t)(N - k) * g.out_sa, x1);
+                }
+            }
+        } else if constexpr (LAST) {
             if (!wok) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
             const bool plain = g.store_mode == ST_C2C && g.tw_dim < 0;
@@ -156,12 +213,12 @@ struct SpecPass {
                 }
             }
             __syncthreads();
-            SpecPass<T, P, S + 1, ALIGNED>::run(g, buf, tid, w_first, wvalid, i1, i2, in_base, out_base);
+            SpecPass<T, P, S + 1, ALIGNED, MODE>::run(g, buf, tid, w_first, wvalid, i1, i2, in_base, out_base);
         }
     }
 };
 
-template <typename T, typename P, bool ALIGNED>
+template <typename T, typename P, bool ALIGNED, int MODE>
 __global__ void __launch_bounds__(P::W *P::TPL, P::MINB) fft_spec_kernel(const TileGeom<T> g) {
     extern __shared__ __align__(16) unsigned char smem_raw_sp[];
     uint32_t t0, i1, i2, rest;
@@ -172,7 +229,7 @@ __global__ void __launch_bounds__(P::W *P::TPL, P::MINB) fft_spec_kernel(const T
     const int wvalid = (int)min((uint32_t)P::W, g.bext[0] - w_first);
     const int64_t in_base = (int64_t)w_first * g.in_bs[0] + (int64_t)i1 * g.in_bs[1] + (int64_t)i2 * g.in_bs[2];
     const int64_t out_base = (int64_t)w_first * g.out_bs[0] + (int64_t)i1 * g.out_bs[1] + (int64_t)i2 * g.out_bs[2];
-    SpecPass<T, P, 0, ALIGNED>::run(g, reinterpret_cast<cx<T> *>(smem_raw_sp), (int)threadIdx.x, w_first, wvalid, i1, i2,
+    SpecPass<T, P, 0, ALIGNED, MODE>::run(g, reinterpret_cast<cx<T> *>(smem_raw_sp), (int)threadIdx.x, w_first, wvalid, i1, i2,
                                     in_base, out_base);
 }
 

@@ -15,6 +15,7 @@ from oracle import pocketfft_oracle as O
 T = parity.reflib() or O
 rng = np.random.default_rng(11)
 bad = 0
+CD = {np.float32: np.complex64, np.float64: np.complex128}
 
 
 def check(name, got, want, dtype, n):
@@ -46,13 +47,16 @@ for dt in (np.complex64, np.complex128):
     check(f"c2c columns in-place {np.dtype(dt).name} (360,37)", got, want, dt, 360)
 # real transforms on jitted lengths
 for dt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
-    for n in (1000, 1001, 1920):
+    for n in (30, 1000, 1001, 1002, 1920):
         x = rng.standard_normal((7, n)).astype(dt)
         got = np.zeros((7, n // 2 + 1), dtype=cdt)
         want = np.zeros_like(got)
+        for fwd in (True, False):  # even n: packed half-length transform + Hermitian unpack (kernel MODE 1)
+            R.r2c(x, got, [1], fwd, 0.25)
+            T.r2c(x, want, [1], fwd, 0.25, 1)
+            check(f"r2c {np.dtype(dt).name} n={n} fwd={fwd}", got, want, dt, n)
         R.r2c(x, got, [1], True, 1.0)
         T.r2c(x, want, [1], True, 1.0, 1)
-        check(f"r2c {np.dtype(dt).name} n={n}", got, want, dt, n)
         back, wback = np.empty_like(x), np.empty_like(x)
         R.c2r(want, back, [1], False, 1.0 / n)
         T.c2r(want, wback, [1], False, 1.0 / n, 1)
@@ -62,5 +66,24 @@ for dt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
     R.r2r_separable_hartley(x, got, [0, 1], 1.0)
     T.r2r_separable_hartley(x, want, [0, 1], 1.0, 1)
     check(f"hartley {np.dtype(dt).name} (1080,48)", got, want, dt, 1080 * 48)
+# zero-padded real lines on the device (n_in < n in the packed load) and a 2-D real transform
+import torch
+
+for dt in (np.float32, np.float64):
+    x = rng.standard_normal((9, 700)).astype(dt)
+    for n in (1000, 1080, 701):
+        xp = np.zeros((9, n), dtype=dt)
+        xp[:, :700] = x
+        want = np.zeros((9, n // 2 + 1), dtype=CD[dt])
+        T.r2c(xp, want, [1], True, 1.0, 1)
+        got = torch.empty((9, n // 2 + 1), dtype=getattr(torch, np.dtype(CD[dt]).name), device="cuda")
+        R.r2c_pad(torch.from_numpy(x).cuda(), got, (9, n), [1], True, 1.0)
+        check(f"r2c_pad {np.dtype(dt).name} 700 -> {n}", got.cpu().numpy(), want, dt, n)
+    x = rng.standard_normal((120, 360)).astype(dt)
+    got = np.zeros((120, 181), dtype=CD[dt])
+    want = np.zeros_like(got)
+    R.r2c(x, got, [0, 1], True, 1.0)
+    T.r2c(x, want, [0, 1], True, 1.0, 1)
+    check(f"rfft2 {np.dtype(dt).name} (120,360)", got, want, dt, 120 * 360)
 print("launches", R.launch_count())
 sys.exit(1 if bad else 0)

@@ -140,6 +140,9 @@ def test_fused_padding_and_cropping_on_device(F):
     R.launch_count_reset()
     F.fft(big, 2048, -1)
     assert R.launch_count() == 1
+    R.launch_count_reset()
+    F.rfft(big.real.contiguous(), 2048, -1)   # packed half-length transform with the padding in its load
+    assert R.launch_count() == 1
     # long padded lines (four-step / gather path) and a non-contiguous input
     x = (rng.standard_normal((3, 70000)) + 1j * rng.standard_normal((3, 70000))).astype(np.complex128)
     d = torch.from_numpy(x).cuda()

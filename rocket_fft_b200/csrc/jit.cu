@@ -282,7 +282,15 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
                   job.n >= 12 && !load_lf && !store_lf && job.is == rsz && ((uintptr_t)job.in % (2 * rsz)) == 0;
     for (auto &d : dims) packed = packed && (d.is % (2 * rsz)) == 0;
     if (packed && regmix_schedule(job.n / 2, job.prec ? 8 : 16).empty() && regmix_schedule(job.n / 2, 16).empty()) packed = false;
-    const int kmode = packed ? 1 : 0;
+    // packed inverse (kernel MODE 2): Hermitian bins (any stride) -> even-length real line
+    bool packed_inv = job.load_mode == LD_HERM && job.store_mode == ST_REAL && job.flags == 0 && job.twN == 0 &&
+                      job.n % 2 == 0 && job.n >= 12 && !load_lf && !store_lf && (job.n_in == 0 || job.n_in == job.n);
+    if (packed_inv && regmix_schedule(job.n / 2, job.prec ? 8 : 16).empty() && regmix_schedule(job.n / 2, 16).empty())
+        packed_inv = false;
+    bool out_vec = ((uintptr_t)job.out % (2 * rsz)) == 0;
+    for (auto &d : dims) out_vec = out_vec && (d.os % (2 * rsz)) == 0;
+    const int kmode = packed ? 1 : (packed_inv ? 2 : 0);
+    packed = packed || packed_inv;  // from here on: geometry in half-length complex points
     const uint64_t n = packed ? job.n / 2 : job.n;
     if (n < 6 || n > 32768 || (n & (n - 1)) == 0) return false;
     if (job.store_mode == ST_HC || job.load_mode >= LD_DCT2 || job.store_mode >= ST_DCT2) return false;
@@ -365,8 +373,9 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
         if (packed) j2.n = n;  // geometry in complex points
         const uint64_t ntiles = fill_geom<T>(g, j2, dims, w, load_lf, store_lf);
         set_prefetch_by_mode<T>(g, job, dims, w);
+        if (kmode == 2) g.flags = out_vec ? 0 : 1;
+        if (kmode == 1) g.n_in = (uint32_t)(job.n_in ? job.n_in : job.n);  // real samples present
         if (packed) {
-            g.n_in = (uint32_t)(job.n_in ? job.n_in : job.n);  // real samples present
             g.twA = (const cx<T> *)get_table(TAB_LINE, job.prec, job.n, 0);
         }
         g.ptw = (const cx<T> *)ptw;

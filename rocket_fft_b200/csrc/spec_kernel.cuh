@@ -6,7 +6,8 @@
 //
 // P must provide:  N, TPL, W, NPASS, MINB (static constexpr int) and static constexpr int radix(int s).
 // MODE 0: complex line job (all load / store modes of line_io.cuh);  MODE 1: packed real -> half spectrum of a
-// contiguous even-length real line (N = half the real length), the structure of MODE 1 in pow2_kernel.cuh.
+// contiguous even-length real line (N = half the real length), the structure of MODE 1 in pow2_kernel.cuh;
+// MODE 2: its inverse, N+1 Hermitian bins -> even-length real line (MODE 2 of pow2_kernel.cuh).
 #pragma once
 #include "common.cuh"
 #include "line_io.cuh"
@@ -70,6 +71,30 @@ struct SpecPass {
                             else if (2u * (uint32_t)e < g.n_in) val.x = *reinterpret_cast<const T *>(line + (int64_t)(2 * e) * sizeof(T));
                         }
                         v[j * R + m] = val;
+                    }
+            } else if (MODE == 2) {
+                // packed inverse real transform: the N+1 Hermitian bins X are folded into the N-point spectrum
+                // Z[e] = (X[e] + conj X[N-e]) + i w^e (X[e] - conj X[N-e]), w = exp(+2 pi i/(2N)), whose backward DFT is
+                // x[2m] + i x[2m+1].  Im X[0], Im X[N] are ignored (H:3830, 3845-3846); forward=true: X -> conj X.
+                const bool cj = g.backward == 0;
+                const int64_t sa = g.in_sa;
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const int e = t + j * TPL + m * IDO;
+                        C z = mk<T>(T(0), T(0));
+                        if (wok && (EXACT || t + j * TPL < NB)) {
+                            C A = ld_cx<T, ALIGNED>(line + (int64_t)e * sa);
+                            C B = ld_cx<T, ALIGNED>(line + (int64_t)(N - e) * sa);
+                            if (e == 0) { A.y = T(0); B.y = T(0); }
+                            if (cj) { A.y = -A.y; B.y = -B.y; }
+                            const C sm = mk<T>(A.x + B.x, A.y - B.y);
+                            const C df = mk<T>(A.x - B.x, A.y + B.y);
+                            const C wd = cmulc(df, __ldg(g.twA + e));  // d * conj(exp(-2 pi i e/(2N)))
+                            z = cswap(mk<T>(sm.x - wd.y, sm.y + wd.x));  // s + i*wd, swapped: backward = swap.forward.swap
+                        }
+                        v[j * R + m] = z;
                     }
             } else if (plain && g.in_sa == (int64_t)sizeof(C)) {
                 const C *p = reinterpret_cast<const C *>(line) + t;
@@ -159,6 +184,29 @@ struct SpecPass {
                 } else {
                     st_cx<T, ALIGNED>(line + (int64_t)k * g.out_sa, x0);
                     st_cx<T, ALIGNED>(line + (int64_t)(N - k) * g.out_sa, x1);
+                }
+            }
+        } else if constexpr (LAST && MODE == 2) {
+            // bins hold swap(x[2k] + i x[2k+1]): deliver the two reals (as one complex store when aligned; flags bit 0
+            // set by the host when the output is not complex-aligned)
+            if (!wok) return;
+            char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
+            const T f = g.fct;
+            const bool vec = g.out_sa == (int64_t)sizeof(T) && g.flags == 0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int b = t + j * TPL;
+                if (EXACT || b < NB) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int k = b + q * NB;
+                        const C val = mk<T>(v[j * R + q].y * f, v[j * R + q].x * f);
+                        if (vec) __stcs(reinterpret_cast<C *>(line) + k, val);
+                        else {
+                            *reinterpret_cast<T *>(line + (int64_t)(2 * k) * g.out_sa) = val.x;
+                            *reinterpret_cast<T *>(line + (int64_t)(2 * k + 1) * g.out_sa) = val.y;
+                        }
+                    }
                 }
             }
         } else if constexpr (LAST) {

@@ -58,9 +58,15 @@ for dt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
         R.r2c(x, got, [1], True, 1.0)
         T.r2c(x, want, [1], True, 1.0, 1)
         back, wback = np.empty_like(x), np.empty_like(x)
-        R.c2r(want, back, [1], False, 1.0 / n)
-        T.c2r(want, wback, [1], False, 1.0 / n, 1)
-        check(f"c2r {np.dtype(dt).name} n={n}", back, wback, dt, n)
+        spec = want + (0.3 + 0.2j)  # non-zero imaginary parts in bin 0 / Nyquist must be ignored
+        for fwd in (False, True):   # even n: Hermitian fold + half-length transform (kernel MODE 2)
+            R.c2r(spec, back, [1], fwd, 1.0 / n)
+            T.c2r(spec, wback, [1], fwd, 1.0 / n, 1)
+            check(f"c2r {np.dtype(dt).name} n={n} fwd={fwd}", back, wback, dt, n)
+        outs = np.zeros((7, 2 * n), dtype=dt)  # strided real output (every other slot)
+        R.c2r(spec, outs[:, ::2], [1], False, 1.0)
+        T.c2r(spec, wback, [1], False, 1.0, 1)
+        check(f"c2r strided out {np.dtype(dt).name} n={n}", outs[:, ::2], wback, dt, n)
     x = rng.standard_normal((1080, 48)).astype(dt)
     got, want = np.empty_like(x), np.empty_like(x)
     R.r2r_separable_hartley(x, got, [0, 1], 1.0)

@@ -133,6 +133,10 @@ def nonpow2():
     run("rfft2 f32 64 x (1080,1920)", lambda: R.r2c(x, X, [1, 2], True, 1.0), nb, None, 5)
     ms = timeit(lambda: torch.fft.rfft2(x), 5)
     report("   cuFFT rfft2 [side ref]", ms, nb)
+    y = torch.empty_like(x)
+    run("irfft2 f32 64 x (1080,1920)", lambda: R.c2r(X, y, [1, 2], False, 1.0), nb, None, 5)
+    ms = timeit(lambda: torch.fft.irfft2(X, s=(1080, 1920)), 5)
+    report("   cuFFT irfft2 [side ref]", ms, nb)
 
 
 ALL = {"nonpow2": nonpow2, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "sizes": sizes}

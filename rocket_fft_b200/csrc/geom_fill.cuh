@@ -114,7 +114,11 @@ inline void set_prefetch_rows(TileGeom<T> &g, const LineJob &job, const std::vec
     // rows further apart than 64 KiB each sit on their own page: the prefetches then cost more (TLB) than they
     // save (measured: 1024^3 c64 axis 1, rows 8 KiB apart: 58 % -> 68 %; axis 0, rows 8 MiB apart: 57 % -> 47 %)
     const int64_t sa = job.is < 0 ? -job.is : job.is;
-    if (pf <= 0 || dims.empty() || dims[0].is != item || n_items > 65536 || sa > 65536) return;
+    static const int64_t max_stride = [] {
+        const char *v = getenv("RFB200_PF_LF_MAXSTRIDE");
+        return v ? (int64_t)atoll(v) : (int64_t)65536;
+    }();
+    if (pf <= 0 || dims.empty() || dims[0].is != item || n_items > 65536 || sa > max_stride) return;
     // zero-padded load (Bluestein): rows whose first element is already past the bound are never read
     if (job.pre_tab && job.g_mul) n_items = std::min<uint64_t>(n_items, (job.pre_bound + job.g_mul - 1) / job.g_mul);
     g.pf_dist = (uint32_t)pf;

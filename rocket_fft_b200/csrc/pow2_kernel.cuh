@@ -146,6 +146,7 @@ struct Pow2Body {
         const int tid = threadIdx.x;
         const bool lf_in = g.load_line_fast != 0, lf_out = g.store_line_fast != 0;
         C v[16];
+        bool staged_in = false;
         prefetch_later_tile<T>(g, (uint32_t)W);
 
         // ---- pass 0: global -> registers -------------------------------------------------
@@ -281,6 +282,20 @@ struct Pow2Body {
                             v[j * R + m] = cmul(val, __ldg(g.pre_tab + gi));
                         }
                     }
+            } else if (MODE == 0 && LOGN <= 6 && (g.stage_io & 1)) {
+                // Short lines, many per CTA (one to four threads per line): read straight into registers, every load
+                // instruction of a warp would touch 32 different 128-byte lines.  The tile is one dense run of
+                // W*N points, so it is copied to shared memory with fully coalesced loads and picked up from there.
+                const C *tile = reinterpret_cast<const C *>(g.in + in_base);
+                const int cnt = wvalid * N;
+                for (int idx = tid; idx < cnt; idx += NT) buf[(idx >> LOGN) * PITCH + (idx & (N - 1))] = __ldcs(tile + idx);
+                __syncthreads();
+                staged_in = true;
+                const C *sl = buf + w * PITCH + t;
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int m = 0; m < R; ++m) v[j * R + m] = wok ? sl[j * TPL + m * ido] : mk<T>(T(0), T(0));
             } else if (packed_vec || (plain && g.in_sa == (int64_t)sizeof(C))) {
                 // contiguous line: one base pointer, compile-time offsets
                 const C *p = reinterpret_cast<const C *>(line) + t;
@@ -325,7 +340,7 @@ struct Pow2Body {
             }
             compute<0>(v, t, stw);
         }
-        bool first = true;
+        bool first = !staged_in;  // false: shared memory is in use, the next writer synchronises first
         if constexpr (PL::NPASS > 1) {
             exchange<1>(v, buf, tid, lf_in, lf_out, first);
             first = false;
@@ -417,6 +432,28 @@ struct Pow2Body {
             return;
         }
         if (MODE == 0 || MODE == 5) {
+            if (MODE == 0 && LOGN <= 6 && (g.stage_io & 2)) {
+                // short lines: through shared memory, then one dense, fully coalesced run of stores (see the load)
+                const T f = g.fct;
+                const bool bw = g.backward != 0;
+                if (!first) __syncthreads();
+                if (w < wvalid) {
+                    C *sl = buf + w * PITCH + t;
+#pragma unroll
+                    for (int j = 0; j < NBL; ++j)
+#pragma unroll
+                        for (int q = 0; q < RL; ++q) {
+                            C val = cscale(v[j * RL + q], f);
+                            if (bw) val = cswap(val);
+                            sl[j * TPL + q * (N / RL)] = val;
+                        }
+                }
+                __syncthreads();
+                C *tile = reinterpret_cast<C *>(g.out + out_base);
+                const int cnt = wvalid * N;
+                for (int idx = tid; idx < cnt; idx += NT) __stcs(tile + idx, buf[(idx >> LOGN) * PITCH + (idx & (N - 1))]);
+                return;
+            }
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
             if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C) && g.split_blk == 0 &&

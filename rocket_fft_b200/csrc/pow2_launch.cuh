@@ -37,6 +37,17 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
         for (auto &d : dims) al = al && (d.os % (int64_t)csz) == 0;
         g.flags = al ? 0 : 1;
     }
+    if (MODE == 0 && (LOGN == 4 || (LOGN == 5 && sizeof(T) == 4)) && W > 1 && !load_lf && !store_lf && !dims.empty()) {
+        // short lines: dense tiles go through shared memory for coalescing (pow2_kernel.cuh).  Measured on B200, % of the
+        // HBM copy peak without -> with staging: c64 n=16 28 -> 88, n=32 46 -> 66, n=64 67 -> 64; c128 n=16 53 -> 75,
+        // n=32 63 -> 56, n=64 80 -> 57: only the first three are switched on.
+        static const bool stage = [] { const char *v = getenv("RFB200_NO_STAGE"); return !(v && atoi(v)); }();
+        const int64_t e = (int64_t)sizeof(cx<T>), line = (int64_t)job.n * e;
+        const bool plain_in = job.load_mode == LD_C2C && (job.n_in == 0 || job.n_in == job.n) && !job.pre_tab;
+        const bool plain_out = job.store_mode == ST_C2C && job.twN == 0 && !job.post_tab && job.split_out.empty();
+        if (stage && plain_in && job.is == e && dims[0].is == line) g.stage_io |= 1;
+        if (stage && plain_out && job.os == e && dims[0].os == line) g.stage_io |= 2;
+    }
     if (load_lf) {
         if (MODE == 0) set_prefetch_by_mode<T>(g, job, dims, (uint32_t)W);
         else if (MODE == 3 || MODE == 4) set_prefetch_rows<T>(g, job, dims, (uint32_t)W, sizeof(T), job.n);

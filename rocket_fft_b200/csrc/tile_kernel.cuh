@@ -45,6 +45,7 @@ struct TileGeom {
     uint32_t n_out;      // number of output slots stored per line
     uint32_t pf_dist, pf_bytes;  // L2 prefetch of the input of the CTA pf_dist tiles ahead (0: off), bytes per tile
     uint32_t pf_rows;            // line-fast tiles: rows of pf_bytes each (0: the tile is one run of pf_bytes)
+    uint32_t stage_io;           // pow2 kernel, short lines: bit 0 / 1 = load / store the dense tile through shared memory
     FastDiv d_nout;
     int backward;        // 1: compute the +i transform through the swap identity
     int64_t in_sa, out_sa;           // axis strides, bytes

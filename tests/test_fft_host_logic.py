@@ -1,0 +1,69 @@
+"""Host-side argument handling of the numpy.fft / scipy.fft style layer (rocket_fft_b200/fft.py): shape / axes
+normalisation, norm -> fct, frequency helpers, next_fast_len.  No GPU needed: nothing here launches a kernel
+(the reference's counterparts: rocket_fft/overloads.py:421-489, 505-551, 1862-1870)."""
+import math
+
+import numpy as np
+import pytest
+import scipy.fft
+
+from rocket_fft_b200 import fft as F
+
+
+def test_shape_and_axes_normalisation():
+    x = np.zeros((4, 5, 6))
+    assert F._shape_axes(x, None, None, True) == ([4, 5, 6], [0, 1, 2])
+    assert F._shape_axes(x, None, None, False) == ([6], [2])
+    assert F._shape_axes(x, (8, 3), None, True) == ([8, 3], [1, 2])
+    assert F._shape_axes(x, None, (-1, 0), True) == ([6, 4], [2, 0])
+    assert F._shape_axes(x, (7, -1), (0, 1), True) == ([7, 5], [0, 1])
+    assert F._shape_axes(x, 9, 1, True) == ([9], [1])
+    with pytest.raises(ValueError):
+        F._shape_axes(x, None, (3,), True)
+    with pytest.raises(ValueError):
+        F._shape_axes(x, (1, 2, 3), (0, 1), True)
+    with pytest.raises(ValueError):
+        F._shape_axes(x, (0,), (0,), True)
+    assert F._target_shape(x, [8, 3], [1, 2]) == [4, 8, 3]
+    assert F._needs_pad(x, [4, 8, 3]) and not F._needs_pad(x, [4, 5, 3])
+    # cropping is a view, zero-padding a copy
+    y = np.arange(24.0).reshape(4, 6)
+    c = F._pad_or_crop(y, [3], [1], np.float64)
+    assert c.shape == (4, 3) and np.shares_memory(c, y)
+    p = F._pad_or_crop(y, [8, 2], [1, 0], np.float64)
+    assert p.shape == (2, 8) and not np.shares_memory(p, y) and np.array_equal(p[:, :6], y[:2]) and not p[:, 6:].any()
+
+
+def test_norm_factors():
+    shape = (4, 5, 6)
+    for axes in ([2], [0, 1], [0, 1, 2], [1, 1]):
+        n = math.prod(shape[a] for a in axes)
+        assert F._fct(shape, axes, None, True) == 1.0 and F._fct(shape, axes, "backward", False) == 1.0 / n
+        assert F._fct(shape, axes, "forward", True) == 1.0 / n and F._fct(shape, axes, "forward", False) == 1.0
+        assert F._fct(shape, axes, "ortho", True) == F._fct(shape, axes, "ortho", False) == 1.0 / math.sqrt(n)
+    # DCT/DST: logical length 2(N + delta) per axis (delta = -1 DCT-I, +1 DST-I, 0 otherwise)
+    assert F._fct(shape, [1], None, False, -1.0) == 1.0 / (2.0 * 4)
+    assert F._fct(shape, [1], None, False, 1.0) == 1.0 / (2.0 * 6)
+    assert F._fct(shape, [0, 2], "ortho", True, 0.0) == 1.0 / math.sqrt(8.0 * 12.0)
+    with pytest.raises(ValueError):
+        F._fct(shape, [0], "nope", True)
+
+
+def test_dtype_promotion_rules():
+    assert F._real_of(np.float16) == np.float32 and F._real_of(np.complex64) == np.float32
+    assert F._real_of(np.int64) == np.float64 and F._real_of(np.complex128) == np.float64 and F._real_of(np.bool_) == np.float64
+    assert F._cplx_of(np.float32) == np.complex64 and F._cplx_of(np.int8) == np.complex128
+
+
+def test_frequencies_and_fast_lengths():
+    for n in (1, 2, 3, 8, 9, 1000, 1001):
+        for d in (1.0, 0.1, 3):
+            assert np.array_equal(F.fftfreq(n, d), np.fft.fftfreq(n, d))
+            assert np.array_equal(F.rfftfreq(n, d), np.fft.rfftfreq(n, d))
+    with pytest.raises(ValueError):
+        F.rfftfreq(0)
+    for t in list(range(0, 300)) + [1000, 1021, 15015, 65537, 1000003]:
+        for real in (False, True):
+            assert F.next_fast_len(t, real) == scipy.fft.next_fast_len(t, real), (t, real)
+    with pytest.raises(ValueError):
+        F.next_fast_len(-1)

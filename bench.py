@@ -252,12 +252,15 @@ def main():
         ]
         peak, peak_src = load_peaks()
         # dominant kernel: the stage with the larger per-launch time
-        per_launch = [(t_row / max(row_launches, 1), row_bytes, "fft_pow2_kernel<float,13,1,1> r2c rows", row_launches),
+        dual = int(os.environ.get("RFB200_DUAL", "1"))
+        row_kernel = ("fft_pow2_dual_kernel<12,1,%s> r2c rows" % ("true" if dual == 2 else "false")) if dual else \
+            "fft_pow2_kernel<float,13,1,1> r2c rows"
+        per_launch = [(t_row / max(row_launches, 1), row_bytes, row_kernel, row_launches),
                       (t_col / max(col_launches, 1), col_bytes, "fft_pow2_kernel<float,7,32,0> four-step column pass", col_launches)]
         dom = max(per_launch, key=lambda p: p[0])
         achieved = dom[1] / (dom[0] * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of that kernel for ONE image, from the
-        # committed `ncu --set full` capture (profiles/r01_ncu_rows_kernel.txt); x images per launch
+        # committed `ncu --set full` capture (profiles/r01_traffic.json names the report); x images per launch
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tpath):

@@ -5,8 +5,55 @@
 
 #include "geom_fill.cuh"
 #include "pow2_kernel.cuh"
+#include "pow2_dual_kernel.cuh"
 
 namespace rfb {
+
+// Long packed real lines (single precision, 16384 reals) as two interleaved half-length transforms per thread
+// (pow2_dual_kernel.cuh).  RFB200_DUAL=0 switches back to the one-transform-per-line register kernel.
+// RFB200_DUAL=2: the variant that composes twiddles instead of loading them one by one.
+inline int dual_variant() {
+    static const int v = [] { const char *e = getenv("RFB200_DUAL"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
+template <int LOGNH, int MODE, bool TWC>
+bool launch_dual_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    using Body = DualBody<LOGNH, MODE, TWC>;
+    // contiguous, fully present lines whose 16-byte {z[2e], z[2e+1]} / {y[2m], y[2m+1]} groups are aligned
+    if (job.n_in != 0 && job.n_in != job.n) return false;
+    if (MODE == 1) {
+        if (job.is != (int64_t)sizeof(float) || ((uint64_t)(uintptr_t)job.in % 16) != 0) return false;
+        for (auto &d : dims) if (d.is % 16) return false;
+    } else {
+        if (job.is != (int64_t)sizeof(float2) || job.os != (int64_t)sizeof(float) || ((uint64_t)(uintptr_t)job.out % 16) != 0) return false;
+        for (auto &d : dims) if (d.os % 16) return false;
+    }
+    TileGeom<float> g;
+    LineJob j2 = job;
+    j2.n = job.n / 2;  // geometry in complex points
+    const uint64_t ntiles = fill_geom<float>(g, j2, dims, 1u, false, false);
+    g.n_out = (uint32_t)(job.n / 2 + 1);
+    g.twA = (const float2 *)get_table(TAB_LINE, job.prec, job.n, 0);
+    if (MODE == 1) {
+        g.n_in = (uint32_t)job.n;
+        set_prefetch<float>(g, job, dims, 1u, sizeof(float), job.n);
+    } else set_prefetch<float>(g, job, dims, 1u, sizeof(float2), job.n / 2 + 1);
+    const float2 *stw = (const float2 *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGNH, 0);
+    const size_t smem = (size_t)Body::PITCH * sizeof(float4);
+    auto kern = fft_pow2_dual_kernel<LOGNH, MODE, TWC>;
+    static thread_local int dev_set = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_set != dev) {
+        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dev_set = dev;
+    }
+    kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
+    count_launch();
+    RFB_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
 
 // lines per CTA: element-fast tiles aim at 256 threads, line-fast tiles at >= 128-byte rows
 constexpr int p2_we(int logn) { return logn <= 10 ? (256 >> (logn - 4)) : (logn == 11 ? 2 : 1); }
@@ -93,6 +140,13 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     }
     if (mode == 1 || mode == 2) {
         if (lf) return false;
+        if constexpr (sizeof(T) == 4 && LOGN == 13) {
+            const int dv = dual_variant();
+            if (dv == 1 && (mode == 1 ? launch_dual_inst<12, 1, false>(job, dims, s) : launch_dual_inst<12, 2, false>(job, dims, s)))
+                return true;
+            if (dv == 2 && (mode == 1 ? launch_dual_inst<12, 1, true>(job, dims, s) : launch_dual_inst<12, 2, true>(job, dims, s)))
+                return true;
+        }
         if (mode == 1) launch_pow2_inst<T, LOGN, WE, 1>(job, dims, load_lf, store_lf, s);
         else launch_pow2_inst<T, LOGN, WE, 2>(job, dims, load_lf, store_lf, s);
         return true;

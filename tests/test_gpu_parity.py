@@ -482,3 +482,69 @@ def test_runtime_specialised_kernels(tmp_path):
     second = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
     assert second.returncode == 0, second.stdout[-3000:] + second.stderr[-3000:]
     assert " from " in second.stderr and "spill=" not in second.stderr, second.stderr[-2000:]
+
+
+def test_long_real_lines_two_transforms_per_thread(R):
+    """16384-point float32 real lines: the kernel that runs two interleaved half-length transforms per thread
+    (pow2_dual_kernel.cuh) on aligned contiguous lines, and the single-transform kernel on everything else --
+    padded rows, shifted (4-byte aligned) views, strided outputs, 3-D batches, both directions, fct != 1,
+    non-zero imaginary DC/Nyquist bins (ignored, H:3830) -- all against the reference."""
+    import torch
+
+    T = trusted()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    n = 16384
+    nb = n // 2 + 1
+
+    def run_r2c(xv, ov, fwd, fct):
+        R.r2c(xv, ov, [xv.dim() - 1], fwd, fct)
+        torch.cuda.synchronize()
+        xh = np.ascontiguousarray(xv.cpu().numpy())
+        want = np.zeros(xh.shape[:-1] + (nb,), dtype=np.complex64)
+        T.r2c(xh, want, [xh.ndim - 1], fwd, fct)
+        check(ov.cpu().numpy(), want, np.float32, n, ("r2c", tuple(xv.shape), tuple(xv.stride()), fwd))
+
+    base = torch.from_numpy(rng.standard_normal((5, 3, n + 16)).astype(np.float32)).to(dev)
+    for xv in (base[..., :n], base[..., 4 : n + 4], base[..., 1 : n + 1], base[:, 1, 8 : n + 8], base[2, 2, :n]):
+        for fwd in (True, False):
+            out = torch.zeros(tuple(xv.shape[:-1]) + (nb,), dtype=torch.complex64, device=dev)
+            run_r2c(xv, out, fwd, 0.25)
+    # strided output bins / padded output rows
+    xv = base[0, :, :n]
+    wide = torch.zeros(3, 2 * nb + 6, dtype=torch.complex64, device=dev)
+    run_r2c(xv, wide[:, 0 : 2 * nb : 2], True, 1.0)
+    run_r2c(xv, wide[:, 3 : 3 + nb], False, 2.0)
+    # 2-D: rows by the two-transform kernel, columns by the four-step passes
+    x2 = torch.from_numpy(rng.standard_normal((64, n)).astype(np.float32)).to(dev)
+    o2 = torch.zeros(64, nb, dtype=torch.complex64, device=dev)
+    R.r2c(x2, o2, [0, 1], True, 1.0)
+    want = np.zeros((64, nb), dtype=np.complex64)
+    T.r2c(x2.cpu().numpy(), want, [0, 1], True, 1.0)
+    check(o2.cpu().numpy(), want, np.float32, 64 * n, "r2c 2-D")
+
+    # ---- c2r ----
+    zh = cplx(rng, (4, 3, nb + 5), np.complex64)
+    z = torch.from_numpy(zh).to(dev)
+    outb = torch.zeros(4, 3, n + 8, dtype=torch.float32, device=dev)
+    for zv in (z[..., :nb], z[..., 2 : nb + 2], z[1, :, 1 : nb + 1]):
+        for ov_full in (outb[..., :n], outb[..., 4 : n + 4], outb[..., 1 : n + 1]):
+            ov = ov_full if zv.dim() == 3 else ov_full[1]
+            for fwd in (True, False):
+                R.c2r(zv, ov, [zv.dim() - 1], fwd, 0.5)
+                torch.cuda.synchronize()
+                zc = np.ascontiguousarray(zv.cpu().numpy())
+                want = np.zeros(zc.shape[:-1] + (n,), dtype=np.float32)
+                T.c2r(zc, want, [zc.ndim - 1], fwd, 0.5)
+                check(ov.cpu().numpy(), want, np.float32, n, ("c2r", tuple(zv.stride()), tuple(ov.stride()), fwd))
+    # round trip of a batch that fills the GPU several times over (every CTA slot, L2 prefetch of later tiles)
+    xb = torch.from_numpy(rng.standard_normal((1200, n)).astype(np.float32)).to(dev)
+    Xb = torch.empty(1200, nb, dtype=torch.complex64, device=dev)
+    R.r2c(xb, Xb, [1], True, 1.0)
+    ref = torch.fft.rfft(xb, dim=1)
+    err = float(torch.linalg.vector_norm((Xb - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
+    assert err < parity.tol(np.float32, n), err
+    yb = torch.empty_like(xb)
+    R.c2r(Xb, yb, [1], False, 1.0 / n)
+    err = float(torch.linalg.vector_norm((yb - xb).double()) / torch.linalg.vector_norm(xb.double()))
+    assert err < parity.tol(np.float32, n), err

@@ -252,7 +252,7 @@ def main():
         ]
         peak, peak_src = load_peaks()
         # dominant kernel: the stage with the larger per-launch time
-        dual = int(os.environ.get("RFB200_DUAL", "1"))
+        dual = int(os.environ.get("RFB200_DUAL", "2"))
         row_kernel = ("fft_pow2_dual_kernel<12,1,%s> r2c rows" % ("true" if dual == 2 else "false")) if dual else \
             "fft_pow2_kernel<float,13,1,1> r2c rows"
         per_launch = [(t_row / max(row_launches, 1), row_bytes, row_kernel, row_launches),

@@ -528,7 +528,92 @@ static void run_via_scratch(const LineJob &job, const std::vector<Dim> &dims, cu
     RFB_AFTER_LAUNCH();
 }
 
+static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+
+// Long strided lines whose intermediate would not fit the L2 cache: both steps in ONE persistent kernel, the
+// intermediate of a strip of neighbouring lines in a ring of L2-resident scratch slots (pow2_fused4_kernel.cuh).
+// Knobs: RFB200_FUSE4 (0: off), RFB200_FUSE4_COLS (lines per strip), RFB200_FUSE4_RING, RFB200_FUSE4_LAG,
+// RFB200_FUSE4_MIN_MB (smallest array that takes this path), RFB200_FUSE4_CHECK (1: synchronise and check).
+static bool fourstep_fused(const LineJob &job, const std::vector<Dim> &dims, uint64_t n1, uint64_t n2, cudaStream_t s) {
+    static const int on = env_int("RFB200_FUSE4", 1);
+    if (!on || job.prec != 0 || n1 != n2 || n1 != 128) return false;
+    if (job.load_mode != LD_C2C || job.store_mode != ST_C2C || job.flags || (job.n_in && job.n_in != job.n) || job.twN ||
+        job.pre_tab || job.post_tab || !job.split_out.empty() || job.conv)
+        return false;
+    if (dims.empty() || dims.size() > 2 || !alignment_ok(job, dims)) return false;
+    const int64_t esz = 8;
+    if (dims[0].is != esz || dims[0].os != esz || iabs64(job.is) <= esz || iabs64(job.os) <= esz) return false;
+    static const int cw_env = env_int("RFB200_FUSE4_COLS", 64);
+    const int64_t CW = std::max(32, (cw_env / 32) * 32);
+    const int64_t cols = dims[0].n, nstr = (cols + CW - 1) / CW, outer = dims.size() == 2 ? dims[1].n : 1;
+    if (cols < CW) return false;
+    // smaller arrays: the two-launch path keeps its intermediate in L2 by itself
+    static const int min_mb = env_int("RFB200_FUSE4_MIN_MB", 96);
+    if ((uint64_t)cols * job.n * (uint64_t)esz < ((uint64_t)min_mb << 20)) return false;
+    const uint64_t S = (uint64_t)outer * (uint64_t)nstr;
+    if (S >= (1u << 20)) return false;
+    static const int ring_env = env_int("RFB200_FUSE4_RING", 4), lag_env = env_int("RFB200_FUSE4_LAG", 2);
+    Fuse4Ctl c;
+    memset(&c, 0, sizeof(c));
+    c.nstrips = (uint32_t)S;
+    c.cols = (uint32_t)cols;
+    c.cw = (uint32_t)CW;
+    c.lag = (uint32_t)std::min<uint64_t>((uint64_t)std::max(lag_env, 1), S);
+    c.ring = (uint32_t)std::max<int64_t>(ring_env, (int64_t)c.lag + 1);
+    c.tiles = (uint32_t)((CW / 32) * (int64_t)n2);
+    c.d_spo = make_fastdiv((uint32_t)nstr);
+    c.in_outer = dims.size() == 2 ? dims[1].is : 0;
+    c.out_outer = dims.size() == 2 ? dims[1].os : 0;
+    c.in_strip = c.out_strip = CW * esz;
+    c.slot_bytes = (int64_t)job.n * CW * esz;
+    const size_t ring_bytes = (size_t)c.ring * (size_t)c.slot_bytes, ctr_bytes = (2 * S + 2) * sizeof(uint32_t);
+    Scratch sc(ring_bytes + ctr_bytes, s);
+    c.ctr = (uint32_t *)((char *)sc.p + ring_bytes);
+    const int64_t s_axis = CW * esz;  // one row of the strip's intermediate: CW neighbouring lines
+    // A: for every residue j0 (mod n2) an n1-point DFT over j1 of x[j1*n2 + j0], times exp(-2 pi i j0 k1 / n),
+    //    stored at slot[k1*n2 + j0][line];  B: for every k1 an n2-point DFT over j0 -> X[k2*n1 + k1]
+    LineJob A, B;
+    A.prec = B.prec = job.prec;
+    A.backward = B.backward = job.backward;
+    A.n = n1;
+    A.is = (int64_t)n2 * job.is;
+    A.os = (int64_t)n2 * s_axis;
+    A.batch = {Dim{CW, esz, esz, false}, Dim{(int64_t)n2, job.is, s_axis, true}};
+    A.in = job.in;
+    A.out = (char *)sc.p;
+    A.fct = 1.0;
+    A.twN = job.n;
+    B.n = n2;
+    B.is = s_axis;
+    B.os = (int64_t)n1 * job.os;
+    B.batch = {Dim{CW, esz, esz, false}, Dim{(int64_t)n1, (int64_t)n2 * s_axis, job.os, false}};
+    B.in = (const char *)sc.p;
+    B.out = job.out;
+    B.fct = job.fct;
+    std::vector<Dim> dA, dB;
+    if (!normalise(A, dA) || !normalise(B, dB)) return false;
+    if (dA.size() != 2 || dB.size() != 2 || dA[0].n != CW || dB[0].n != CW) return false;
+    RFB_CUDA_CHECK(cudaMemsetAsync(c.ctr, 0, ctr_bytes, s));
+    if (!launch_fourstep_fused_f32(A, dA, B, dB, c, s)) return false;
+    static const int check = env_int("RFB200_FUSE4_CHECK", 0);
+    if (check) {
+        // debugging aid: a dependency that was never satisfied shows up as ctr[1] != 0 (the kernel does not hang)
+        uint32_t flag = 0;
+        RFB_CUDA_CHECK(cudaMemcpyAsync(&flag, c.ctr + 1, sizeof(flag), cudaMemcpyDeviceToHost, s));
+        RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (flag) { set_error("fused four-step: a tile waited for a dependency that never completed"); throw Error(); }
+    }
+    return true;
+}
+
 static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    uint64_t n1, n2;
+    choose_split(job.n, job.prec, n1, n2);
+    if (fourstep_fused(job, dims, n1, n2, s)) return;
+    run_fourstep_plain(job, dims, s);
+}
+
+static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
     const int64_t esz = job.prec ? 16 : 8;
     uint64_t n1, n2;
     choose_split(job.n, job.prec, n1, n2);

@@ -147,6 +147,9 @@ inline void set_prefetch_by_mode(TileGeom<T> &g, const LineJob &job, const std::
 // pow2_launch_*.cu: returns false when the job is not one the register kernel takes
 bool launch_pow2_f32(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s);
 bool launch_pow2_f64(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s);
+// pow2_launch_f32.cu: fused four-step (both steps in one persistent kernel, intermediate in L2); false if not taken
+bool launch_fourstep_fused_f32(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB,
+                               const Fuse4Ctl &c, cudaStream_t s);
 // jit.cu: run-time specialised kernel for smooth non-power-of-two lengths (NVRTC); false if not taken
 bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
                      cudaStream_t s);

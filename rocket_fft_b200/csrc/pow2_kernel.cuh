@@ -22,6 +22,36 @@
 
 namespace rfb {
 
+// L2 cache policies for the fused four-step kernel (pow2_fused4_kernel.cuh): the scratch ring is kept in L2
+// (evict_last), the array itself streams through (evict_first); neither side allocates in L1 (another CTA
+// rewrites the scratch, a stale L1 line must never be hit).
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float2 ld_policy(const float2 *p, uint64_t pol) {
+    float2 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ double2 ld_policy(const double2 *p, uint64_t pol) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_policy(float2 *p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_policy(double2 *p, double2 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
 template <int LOGN>
 struct P2 {
     static constexpr int N = 1 << LOGN;
@@ -136,18 +166,31 @@ struct Pow2Body {
     }
 
     static __device__ __forceinline__ void run(const TileGeom<T> &g, const C *__restrict__ stw, C *buf) {
+        run_tile<0>(g, stw, buf, blockIdx.x, 0, 0, g.bext[0]);
+    }
+
+    // POL 0: one tile per CTA (tile = blockIdx.x).  POL 1 / 2: steps A / B of the fused four-step kernel -- the
+    // tile index and the byte offsets of the current strip come from the caller; strided plain loads and strided
+    // complex stores carry L2 policies (1: array -> scratch ring, 2: scratch ring -> array); ext0 = lines of the
+    // tile dim that exist in this strip (the caller skips tiles that lie entirely beyond it).
+    template <int POL>
+    static __device__ __forceinline__ void run_tile(const TileGeom<T> &g, const C *__restrict__ stw, C *buf, uint32_t tile,
+                                                    int64_t in_off, int64_t out_off, uint32_t ext0) {
         uint32_t t0, i1, i2, rest;
-        fdivmod(blockIdx.x, g.d_t0, rest, t0);
+        fdivmod(tile, g.d_t0, rest, t0);
         fdivmod(rest, g.d_e1, i2, i1);
         const uint32_t w_first = t0 * W;
-        const int wvalid = (int)min((uint32_t)W, g.bext[0] - w_first);
-        const int64_t in_base = (int64_t)w_first * g.in_bs[0] + (int64_t)i1 * g.in_bs[1] + (int64_t)i2 * g.in_bs[2];
-        const int64_t out_base = (int64_t)w_first * g.out_bs[0] + (int64_t)i1 * g.out_bs[1] + (int64_t)i2 * g.out_bs[2];
+        const int wvalid = (int)min((uint32_t)W, ext0 - w_first);
+        const int64_t in_base = in_off + (int64_t)w_first * g.in_bs[0] + (int64_t)i1 * g.in_bs[1] + (int64_t)i2 * g.in_bs[2];
+        const int64_t out_base = out_off + (int64_t)w_first * g.out_bs[0] + (int64_t)i1 * g.out_bs[1] + (int64_t)i2 * g.out_bs[2];
         const int tid = threadIdx.x;
         const bool lf_in = g.load_line_fast != 0, lf_out = g.store_line_fast != 0;
         C v[16];
         bool staged_in = false;
-        prefetch_later_tile<T>(g, (uint32_t)W);
+        uint64_t pol_in = 0, pol_out = 0;
+        if constexpr (POL == 1) { pol_in = l2_policy_stream(); pol_out = l2_policy_keep(); }
+        if constexpr (POL == 2) { pol_in = l2_policy_keep(); pol_out = l2_policy_stream(); }
+        if constexpr (POL == 0) prefetch_later_tile<T>(g, (uint32_t)W);
 
         // ---- pass 0: global -> registers -------------------------------------------------
         {
@@ -313,7 +356,8 @@ struct Pow2Body {
                     const char *pm = pj;
 #pragma unroll
                     for (int m = 0; m < R; ++m) {
-                        v[j * R + m] = wok ? *reinterpret_cast<const C *>(pm) : mk<T>(T(0), T(0));
+                        if constexpr (POL != 0) v[j * R + m] = wok ? ld_policy(reinterpret_cast<const C *>(pm), pol_in) : mk<T>(T(0), T(0));
+                        else v[j * R + m] = wok ? *reinterpret_cast<const C *>(pm) : mk<T>(T(0), T(0));
                         pm += step_m;
                     }
                     pj += step_j;
@@ -514,7 +558,8 @@ struct Pow2Body {
                             const uint32_t k = (uint32_t)(t + j * TPL + q * (N / RL));
                             char *dst = g.split_base[fdiv(k, g.d_split)] + (pq - g.out);
                             *reinterpret_cast<C *>(dst) = val;
-                        } else *reinterpret_cast<C *>(pq) = val;
+                        } else if constexpr (POL != 0) st_policy(reinterpret_cast<C *>(pq), val, pol_out);
+                        else *reinterpret_cast<C *>(pq) = val;
                         pq += step_q;
                     }
                     pj += step_j;

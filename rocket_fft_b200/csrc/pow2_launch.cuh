@@ -6,6 +6,7 @@
 #include "geom_fill.cuh"
 #include "pow2_kernel.cuh"
 #include "pow2_dual_kernel.cuh"
+#include "pow2_fused4_kernel.cuh"
 
 namespace rfb {
 
@@ -175,6 +176,47 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
         launch_pow2_inst<T, LOGN, WL, 0>(job, dims, load_lf, store_lf, s);
         return true;
     }
+}
+
+// Both steps of a four-step transform of strided lines in one persistent kernel (pow2_fused4_kernel.cuh).
+// A, B: the two line jobs for ONE strip (strip 0 of outer item 0), already normalised; c: everything except the
+// geometry.  false (nothing launched) when there is no instantiation for this length.
+template <typename T, int LOGN>
+bool launch_fused4_logn(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB, Fuse4Ctl c,
+                        cudaStream_t s) {
+    constexpr int W = p2_wl(LOGN, sizeof(T) == 8);
+    using Body = Pow2Body<T, LOGN, W, 0>;
+    TileGeom<T> gA, gB;
+    const uint64_t tA = fill_geom<T>(gA, A, dA, (uint32_t)W, true, true);
+    const uint64_t tB = fill_geom<T>(gB, B, dB, (uint32_t)W, true, true);
+    if (tA != tB || tA != c.tiles) return false;
+    c.d_tiles = make_fastdiv(c.tiles);
+    const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, A.prec, 1ull << LOGN, 0);
+    const size_t smem = (size_t)W * Body::PITCH * sizeof(cx<T>);
+    auto kern = fft_fourstep_fused_kernel<T, LOGN, W>;
+    static thread_local int dev_set = -1;
+    static thread_local int sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_set != dev) {
+        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RFB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        dev_set = dev;
+    }
+    const uint64_t items = 2ull * c.nstrips * c.tiles;
+    const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)sms * p2_min_blocks<T, Body::NT>());
+    kern<<<grid, Body::NT, smem, s>>>(gA, gB, stw, c);
+    count_launch();
+    RFB_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+template <typename T>
+bool launch_fused4_any(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB, const Fuse4Ctl &c,
+                       cudaStream_t s) {
+    if (A.n != B.n || dA.size() > (size_t)MAXB || dB.size() > (size_t)MAXB) return false;
+    if (sizeof(T) == 4 && A.n == 128) return launch_fused4_logn<T, 7>(A, dA, B, dB, c, s);
+    return false;
 }
 
 template <typename T, int MAXLOG>

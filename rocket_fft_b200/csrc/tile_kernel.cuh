@@ -73,6 +73,18 @@ struct TileGeom {
     int pre_swap, post_swap;
 };
 
+// control block of the fused four-step kernel (pow2_fused4_kernel.cuh)
+struct Fuse4Ctl {
+    uint32_t nstrips;        // strips in total (outer batch x strips per outer item)
+    uint32_t cols, cw;       // neighbouring lines per outer item / per strip (the last strip of an item may be narrower)
+    uint32_t tiles;          // tiles per strip and step
+    uint32_t ring, lag;      // scratch slots; distance (in strips) between A(s) and B(s) in the ticket order
+    FastDiv d_tiles, d_spo;  // item -> (unit, tile); strip -> (outer, strip within outer item)
+    int64_t in_outer, in_strip, out_outer, out_strip;  // byte offsets on the array side
+    int64_t slot_bytes;
+    uint32_t *ctr;           // [0] ticket, [1] error flag, [2 .. 2+S) tiles of A(s) done, [2+S .. 2+2S) tiles of B(s) done
+};
+
 // The CTAs resident on an SM tend to load, compute and store in step, which leaves HBM idle while they compute.
 // One thread asks the L2 to fetch the input of the tile that will run pf_dist tiles from now (one bulk-prefetch
 // instruction for the whole tile): DRAM streams in the background and the later CTA's loads hit L2.

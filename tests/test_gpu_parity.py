@@ -548,3 +548,39 @@ def test_long_real_lines_two_transforms_per_thread(R):
     R.c2r(Xb, yb, [1], False, 1.0 / n)
     err = float(torch.linalg.vector_norm((yb - xb).double()) / torch.linalg.vector_norm(xb.double()))
     assert err < parity.tol(np.float32, n), err
+
+
+def test_fused_fourstep_long_strided_lines(R):
+    """16384-point complex64 lines along a strided axis of arrays larger than the L2 cache: both four-step passes run
+    in one persistent kernel with the intermediate in an L2-resident scratch ring (pow2_fused4_kernel.cuh).  Widths that
+    are not multiples of the strip / tile width, a batch of arrays, in place and out of place, both directions,
+    fct != 1 -- against the reference on the host."""
+    import torch
+
+    T = trusted()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(12)
+    n = 16384
+    for shape, axis in (((n, 777), 0), ((2, n, 800), 1), ((n, 1025), 0)):
+        xh = cplx(rng, shape, np.complex64)
+        x = torch.from_numpy(xh).to(dev)
+        for fwd, fct, inplace in ((True, 1.0, False), (False, 0.5, True)):
+            want = np.empty_like(xh)
+            T.c2c(xh, want, [axis], fwd, fct)
+            src = x.clone()
+            out = src if inplace else torch.empty_like(src)
+            R.c2c(src, out, [axis], fwd, fct)
+            torch.cuda.synchronize()
+            check(out.cpu().numpy(), want, np.float32, n, ("fused four-step", shape, fwd, inplace))
+            if not inplace:
+                assert torch.equal(src, x)  # the input is left alone
+    # output with a different row pitch than the input (the c2r path transforms into a contiguous temporary)
+    wide = torch.zeros(n, 900, dtype=torch.complex64, device=dev)
+    xh = cplx(rng, (n, 801), np.complex64)
+    x = torch.from_numpy(xh).to(dev)
+    R.c2c(x, wide[:, 7 : 7 + 801], [0], True, 1.0)
+    torch.cuda.synchronize()
+    want = np.empty_like(xh)
+    T.c2c(xh, want, [0], True, 1.0)
+    check(wide[:, 7 : 7 + 801].cpu().numpy(), want, np.float32, n, "fused four-step, different pitches")
+    assert float(wide[:, :7].abs().max()) == 0.0 and float(wide[:, 808:].abs().max()) == 0.0

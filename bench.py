@@ -256,7 +256,9 @@ def main():
         row_kernel = ("fft_pow2_dual_kernel<12,1,%s> r2c rows" % ("true" if dual == 2 else "false")) if dual else \
             "fft_pow2_kernel<float,13,1,1> r2c rows"
         per_launch = [(t_row / max(row_launches, 1), row_bytes, row_kernel, row_launches),
-                      (t_col / max(col_launches, 1), col_bytes, "fft_pow2_kernel<float,7,32,0> four-step column pass", col_launches)]
+                      (t_col / max(col_launches, 1), col_bytes,
+                       "fft_fourstep_fused_kernel<float,7,32> columns (both four-step passes, intermediate in L2)" if col_launches == 1
+                       else "fft_pow2_kernel<float,7,32,0> four-step column pass", col_launches)]
         dom = max(per_launch, key=lambda p: p[0])
         achieved = dom[1] / (dom[0] * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of that kernel for ONE image, from the
@@ -266,7 +268,7 @@ def main():
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
-                key = "rows" if dom[2].endswith("r2c rows") else "cols_pass"
+                key = "rows" if dom[2].endswith("r2c rows") else ("cols_fused" if "fused" in dom[2] else "cols_pass")
                 traffic = tj[key]["dram_bytes_per_image"] * B
             except Exception:
                 traffic = None

@@ -28,49 +28,86 @@ __global__ void __launch_bounds__(W *(1 << LOGN) / 16, p2_min_blocks<T, W *(1 <<
     using Body = Pow2Body<T, LOGN, W, 0>;
     extern __shared__ __align__(16) unsigned char smem_raw_f4[];
     cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw_f4);
-    __shared__ uint32_t s_item;
+    // Tickets are drawn two tiles ahead and the next tile's dependency is probed while the current tile runs, so that in
+    // the steady state a CTA goes from one tile to the next through a single barrier.  (A CTA may hold up to three
+    // tickets; it works them off in order, and the smallest unfinished ticket never depends on a larger one.)
+    __shared__ uint32_t s_item[3], s_ready[3];
     const uint32_t S = c.nstrips, lag = c.lag;
     const uint32_t total_units = 2 * S;
-    for (;;) {
-        __syncthreads();  // the previous tile is out of shared memory; s_item may be overwritten
-        if (threadIdx.x == 0) s_item = atomicAdd(&c.ctr[0], 1u);
-        __syncthreads();
-        uint32_t unit, tile;
-        fdivmod(s_item, c.d_tiles, unit, tile);
-        if (unit >= total_units) return;
-        // unit -> (step, strip): A(0..lag-1), then pairs A(lag + i), B(i), then the last B's
-        uint32_t strip;
-        bool stepB;
+    // item -> (step, strip, tile); unit order: A(0..lag-1), then pairs A(lag + i), B(i), then the last B's
+    auto decode = [&](uint32_t item, bool &stepB, uint32_t &strip, uint32_t &tile) -> bool {
+        uint32_t unit;
+        fdivmod(item, c.d_tiles, unit, tile);
+        if (unit >= total_units) return false;
         if (unit < lag) { stepB = false; strip = unit; }
         else if (unit < lag + 2 * (S - lag)) { const uint32_t v = unit - lag; stepB = (v & 1u) != 0; strip = stepB ? (v >> 1) : lag + (v >> 1); }
         else { stepB = true; strip = S - lag + (unit - lag - 2 * (S - lag)); }
-        // dependencies
+        return true;
+    };
+    // the counter a tile waits for (nullptr: none): B(s) needs all of A(s) written, A(s) needs B(s - ring) to have read the slot
+    auto dep_flag = [&](bool stepB, uint32_t strip) -> const uint32_t * {
+        if (stepB) return c.ctr + 2 + strip;
+        if (strip >= c.ring) return c.ctr + 2 + S + (strip - c.ring);
+        return nullptr;
+    };
+    if (threadIdx.x == 0) {
+        s_item[0] = atomicAdd(&c.ctr[0], 1u);
+        s_item[1] = atomicAdd(&c.ctr[0], 1u);
+        s_ready[0] = 0;
+        s_ready[1] = 0;
+    }
+    __syncthreads();
+    for (uint32_t slot = 0;; slot = (slot == 2 ? 0 : slot + 1)) {
+        const uint32_t slot1 = (slot == 2 ? 0 : slot + 1), slot2 = (slot1 == 2 ? 0 : slot1 + 1);
+        bool stepB;
+        uint32_t strip, tile;
+        if (!decode(s_item[slot], stepB, strip, tile)) return;
+        const bool ready = s_ready[slot] != 0;
+        uint32_t t2 = 0, nflag = 0;
         if (threadIdx.x == 0) {
-            const uint32_t *flag = nullptr;
-            if (stepB) flag = c.ctr + 2 + strip;                              // all of A(strip) written
-            else if (strip >= c.ring) flag = c.ctr + 2 + S + (strip - c.ring);  // B(strip - ring) has read the slot
-            if (flag) {
-                // never hang the GPU: after ~1 s without progress flag an error (ctr[1]) and stop waiting
-                uint32_t spins = 0;
-                while (ld_acquire_u32(flag) < c.tiles) {
-                    __nanosleep(200);
-                    if (++spins > (1u << 22) || ld_acquire_u32(c.ctr + 1) != 0) { atomicExch(&c.ctr[1], 1u); break; }
-                }
+            t2 = atomicAdd(&c.ctr[0], 1u);  // ticket of the tile after the next; consumed at the end of this tile
+            bool nB;
+            uint32_t nstrip, ntile;
+            nflag = c.tiles;
+            if (decode(s_item[slot1], nB, nstrip, ntile)) {
+                const uint32_t *nf = dep_flag(nB, nstrip);
+                if (nf) nflag = ld_acquire_u32(nf);  // probe of the next tile's dependency, also consumed at the end
             }
         }
-        __syncthreads();
-        uint32_t outer, sw, trest, t0;
+        if (!ready) {
+            if (threadIdx.x == 0) {
+                const uint32_t *flag = dep_flag(stepB, strip);
+                if (flag) {
+                    // never hang the GPU: after ~1 s without progress flag an error (ctr[1]) and stop waiting
+                    uint32_t spins = 0;
+                    while (ld_acquire_u32(flag) < c.tiles) {
+                        __nanosleep(200);
+                        if (++spins > (1u << 22) || ld_acquire_u32(c.ctr + 1) != 0) { atomicExch(&c.ctr[1], 1u); break; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        uint32_t outer, sw, trest, t0, ringq, slot_i;
         fdivmod(strip, c.d_spo, outer, sw);
         fdivmod(tile, gA.d_t0, trest, t0);
+        fdivmod(strip, c.d_ring, ringq, slot_i);
         const uint32_t ext0 = min(c.cw, c.cols - sw * c.cw);  // the last strip of an outer item may be narrower
-        const int64_t slot = (int64_t)(strip % c.ring) * c.slot_bytes;
+        const int64_t sbytes = (int64_t)slot_i * c.slot_bytes;
         if (t0 * (uint32_t)W < ext0) {
-            if (!stepB) Body::template run_tile<1>(gA, stw, buf, tile, (int64_t)outer * c.in_outer + (int64_t)sw * c.in_strip, slot, ext0);
-            else Body::template run_tile<2>(gB, stw, buf, tile, slot, (int64_t)outer * c.out_outer + (int64_t)sw * c.out_strip, ext0);
+            if (!stepB) Body::template run_tile<1>(gA, stw, buf, tile, (int64_t)outer * c.in_outer + (int64_t)sw * c.in_strip, sbytes, ext0);
+            else Body::template run_tile<2>(gB, stw, buf, tile, sbytes, (int64_t)outer * c.out_outer + (int64_t)sw * c.out_strip, ext0);
         }
-        __threadfence();  // this thread's stores are visible GPU-wide before the tile is counted as done
-        __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(&c.ctr[2 + (stepB ? S : 0) + strip], 1u);
+        if (threadIdx.x == 0) {
+            s_item[slot2] = t2;
+            s_ready[slot1] = nflag >= c.tiles ? 1u : 0u;
+        }
+        __syncthreads();  // every thread's stores are issued; shared memory and the control slots are free again
+        if (threadIdx.x == 0) {
+            // release: the CTA's stores (ordered before this thread by the barrier) become visible GPU-wide first
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            atomicAdd(&c.ctr[2 + (stepB ? S : 0) + strip], 1u);
+        }
     }
 }
 

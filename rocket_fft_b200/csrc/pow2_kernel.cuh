@@ -299,7 +299,7 @@ struct Pow2Body {
                         v[idx] = cswap(mk<T>(s.x - wd.y, s.y + wd.x));
                     }
                 }
-            } else if (MODE == 0 && g.pre_tab != nullptr) {
+            } else if (POL == 0 && MODE == 0 && g.pre_tab != nullptr) {
                 // zero-padded load with a fused element-wise factor (Bluestein's chirp): global index
                 // gi = e * g_mul + c * c_mul decides both the padding and the table entry
                 const uint32_t c = (g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2))) * g.c_mul;
@@ -325,7 +325,7 @@ struct Pow2Body {
                             v[j * R + m] = cmul(val, __ldg(g.pre_tab + gi));
                         }
                     }
-            } else if (MODE == 0 && LOGN <= 6 && (g.stage_io & 1)) {
+            } else if (POL == 0 && MODE == 0 && LOGN <= 6 && (g.stage_io & 1)) {
                 // Short lines, many per CTA (one to four threads per line): read straight into registers, every load
                 // instruction of a warp would touch 32 different 128-byte lines.  The tile is one dense run of
                 // W*N points, so it is copied to shared memory with fully coalesced loads and picked up from there.
@@ -339,14 +339,14 @@ struct Pow2Body {
                 for (int j = 0; j < NB; ++j)
 #pragma unroll
                     for (int m = 0; m < R; ++m) v[j * R + m] = wok ? sl[j * TPL + m * ido] : mk<T>(T(0), T(0));
-            } else if (packed_vec || (plain && g.in_sa == (int64_t)sizeof(C))) {
+            } else if (POL == 0 && (packed_vec || (plain && g.in_sa == (int64_t)sizeof(C)))) {
                 // contiguous line: one base pointer, compile-time offsets
                 const C *p = reinterpret_cast<const C *>(line) + t;
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
 #pragma unroll
                     for (int m = 0; m < R; ++m) v[j * R + m] = wok ? __ldcs(p + j * TPL + m * ido) : mk<T>(T(0), T(0));
-            } else if (plain) {
+            } else if (POL != 0 || plain) {  // (the fused four-step kernel only ever takes this path)
                 // strided line: running pointers instead of a 64-bit multiply per element
                 const int64_t sa = g.in_sa;
                 const int64_t step_m = (int64_t)ido * sa, step_j = (int64_t)TPL * sa;
@@ -476,7 +476,7 @@ struct Pow2Body {
             return;
         }
         if (MODE == 0 || MODE == 5) {
-            if (MODE == 0 && LOGN <= 6 && (g.stage_io & 2)) {
+            if (POL == 0 && MODE == 0 && LOGN <= 6 && (g.stage_io & 2)) {
                 // short lines: through shared memory, then one dense, fully coalesced run of stores (see the load)
                 const T f = g.fct;
                 const bool bw = g.backward != 0;
@@ -500,7 +500,7 @@ struct Pow2Body {
             }
             if (w >= wvalid) return;
             char *line = g.out + out_base + (int64_t)w * g.out_bs[0];
-            if (g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C) && g.split_blk == 0 &&
+            if (POL == 0 && g.store_mode == ST_C2C && g.tw_dim < 0 && g.out_sa == (int64_t)sizeof(C) && g.split_blk == 0 &&
                 g.post_tab == nullptr) {
                 const T f = g.fct;
                 const bool bw = (MODE == 5) || g.backward != 0;
@@ -515,12 +515,12 @@ struct Pow2Body {
                     }
                 return;
             }
-            if (g.store_mode == ST_C2C) {
+            if (POL != 0 || g.store_mode == ST_C2C) {
                 // strided output, optionally with the four-step factor exp(-2 pi i c k / bigN):
                 // exact two-level table look-ups for every 4th bin, three recurrence steps between
                 const T f = g.fct;
                 const bool bw = (MODE == 5) || g.backward != 0;
-                const bool tw = g.tw_dim >= 0;
+                const bool tw = (POL == 2) ? false : g.tw_dim >= 0;  // fused four-step: step A has the factor, step B not
                 const uint32_t c = tw ? ((g.tw_dim == 0) ? (w_first + w) : (g.tw_dim == 1 ? i1 : i2)) : 0u;
                 auto lookup = [&](uint32_t x) {
                     uint32_t hi, lo;
@@ -545,7 +545,7 @@ struct Pow2Body {
                         }
                         val = cscale(val, f);
                         if (bw) val = cswap(val);
-                        if (g.post_tab != nullptr) {
+                        if (POL == 0 && g.post_tab != nullptr) {
                             // fused element-wise factor / truncation on the way out (Bluestein)
                             const uint32_t cc = (g.c_dim < 0 ? 0u : ((g.c_dim == 0) ? (w_first + w) : (g.c_dim == 1 ? i1 : i2))) * g.c_mul;
                             const uint32_t bin = (uint32_t)(t + j * TPL + q * (N / RL)) * g.g_mul + cc;
@@ -553,7 +553,7 @@ struct Pow2Body {
                             val = cmul(val, __ldg(g.post_tab + bin));
                             if (g.post_swap) val = cswap(val);
                         }
-                        if (g.split_blk) {
+                        if (POL == 0 && g.split_blk) {
                             // fused exchange: the bin's block decides which (peer) buffer receives it
                             const uint32_t k = (uint32_t)(t + j * TPL + q * (N / RL));
                             char *dst = g.split_base[fdiv(k, g.d_split)] + (pq - g.out);

@@ -191,6 +191,7 @@ bool launch_fused4_logn(const LineJob &A, const std::vector<Dim> &dA, const Line
     const uint64_t tB = fill_geom<T>(gB, B, dB, (uint32_t)W, true, true);
     if (tA != tB || tA != c.tiles) return false;
     c.d_tiles = make_fastdiv(c.tiles);
+    c.d_ring = make_fastdiv(c.ring);
     const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, A.prec, 1ull << LOGN, 0);
     const size_t smem = (size_t)W * Body::PITCH * sizeof(cx<T>);
     auto kern = fft_fourstep_fused_kernel<T, LOGN, W>;

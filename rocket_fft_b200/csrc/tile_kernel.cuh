@@ -79,7 +79,7 @@ struct Fuse4Ctl {
     uint32_t cols, cw;       // neighbouring lines per outer item / per strip (the last strip of an item may be narrower)
     uint32_t tiles;          // tiles per strip and step
     uint32_t ring, lag;      // scratch slots; distance (in strips) between A(s) and B(s) in the ticket order
-    FastDiv d_tiles, d_spo;  // item -> (unit, tile); strip -> (outer, strip within outer item)
+    FastDiv d_tiles, d_spo, d_ring;  // item -> (unit, tile); strip -> (outer, strip within outer item); strip -> slot
     int64_t in_outer, in_strip, out_outer, out_strip;  // byte offsets on the array side
     int64_t slot_bytes;
     uint32_t *ctr;           // [0] ticket, [1] error flag, [2 .. 2+S) tiles of A(s) done, [2+S .. 2+2S) tiles of B(s) done

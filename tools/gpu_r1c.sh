@@ -15,7 +15,7 @@ run() { echo "-- $*"; env "$@" timeout 120 python tools/microbench.py cfg2 2>&1 
   run RFB200_FUSE4_COLS=256 RFB200_FUSE4_RING=4 RFB200_FUSE4_LAG=2
   run RFB200_FUSE4_COLS=64 RFB200_FUSE4_RING=6 RFB200_FUSE4_LAG=3
   run RFB200_FUSE4_COLS=128 RFB200_FUSE4_RING=6 RFB200_FUSE4_LAG=3
-  run RFB200_FUSE4_COLS=32 RFB200_FUSE4_RING=8 RFB200_FUSE4_LAG=4
+  run RFB200_FUSE4_COLS=96 RFB200_FUSE4_RING=5 RFB200_FUSE4_LAG=2
   run RFB200_FUSE4_COLS=128 RFB200_FUSE4_RING=3 RFB200_FUSE4_LAG=1 ) 2>&1 | tee $O/r1c_sweep_fuse4.log
 echo "== bench default"
 timeout 300 python bench.py > $O/r1c_bench_1gpu.json 2> $O/r1c_bench_1gpu.err

@@ -532,10 +532,15 @@ static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims,
 
 // Long strided lines whose intermediate would not fit the L2 cache: both steps in ONE persistent kernel, the
 // intermediate of a strip of neighbouring lines in a ring of L2-resident scratch slots (pow2_fused4_kernel.cuh).
-// Knobs: RFB200_FUSE4 (0: off), RFB200_FUSE4_COLS (lines per strip), RFB200_FUSE4_RING, RFB200_FUSE4_LAG,
+// Knobs: RFB200_FUSE4 (1: on), RFB200_FUSE4_COLS (lines per strip), RFB200_FUSE4_RING, RFB200_FUSE4_LAG,
 // RFB200_FUSE4_MIN_MB (smallest array that takes this path), RFB200_FUSE4_CHECK (1: synchronise and check).
 static bool fourstep_fused(const LineJob &job, const std::vector<Dim> &dims, uint64_t n1, uint64_t n2, cudaStream_t s) {
-    static const int on = env_int("RFB200_FUSE4", 1);
+    // Off by default.  Measured on B200 (16384 x 8193 complex64 columns, profiles/r01c_*): the ring does stay in L2 (DRAM
+    // traffic 2.37 GB instead of 4.3 GB) but the column transform takes 0.90-0.97 ms against 0.82 ms for the two launches:
+    // the 128-point line-fast tiles are limited by instruction issue and load latency on the SM, not by DRAM, so halving
+    // the DRAM traffic buys nothing until the tile body itself is leaner.  (Read per call so that tests can switch it.)
+    const char *on_env = getenv("RFB200_FUSE4");
+    const int on = on_env ? atoi(on_env) : 0;
     if (!on || job.prec != 0 || n1 != n2 || n1 != 128) return false;
     if (job.load_mode != LD_C2C || job.store_mode != ST_C2C || job.flags || (job.n_in && job.n_in != job.n) || job.twN ||
         job.pre_tab || job.post_tab || !job.split_out.empty() || job.conv)

@@ -561,6 +561,19 @@ def test_fused_fourstep_long_strided_lines(R):
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(12)
     n = 16384
+    os.environ["RFB200_FUSE4"] = "1"  # opt-in path (read per call); the same cases without it run in the last loop
+    os.environ["RFB200_FUSE4_CHECK"] = "1"
+    try:
+        _fused_fourstep_cases(R, T, dev, rng, n)
+        assert R.launch_count() > 0
+    finally:
+        os.environ.pop("RFB200_FUSE4", None)
+    _fused_fourstep_cases(R, T, dev, rng, n)
+
+
+def _fused_fourstep_cases(R, T, dev, rng, n):
+    import torch
+
     for shape, axis in (((n, 777), 0), ((2, n, 800), 1), ((n, 1025), 0)):
         xh = cplx(rng, shape, np.complex64)
         x = torch.from_numpy(xh).to(dev)

@@ -7,6 +7,7 @@
 #include "pow2_kernel.cuh"
 #include "pow2_dual_kernel.cuh"
 #include "pow2_fused4_kernel.cuh"
+#include "pow2_pair_kernel.cuh"
 
 namespace rfb {
 
@@ -127,6 +128,9 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
     RFB_CUDA_CHECK(cudaGetLastError());
 }
 
+template <int LOGN, int W>
+bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+
 template <typename T, int LOGN>
 bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, int mode,
                       cudaStream_t s) {
@@ -173,9 +177,42 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     }
     if constexpr (WL == 0) return false;
     else {
+        if constexpr (sizeof(T) == 4 && LOGN >= 7 && LOGN <= 10 && WL >= 2) {
+            if (load_lf && store_lf && launch_pair_inst<LOGN, WL>(job, dims, s)) return true;
+        }
         launch_pow2_inst<T, LOGN, WL, 0>(job, dims, load_lf, store_lf, s);
         return true;
     }
+}
+
+// Strided float32 lines whose neighbours are adjacent on both sides: two lines per thread (pow2_pair_kernel.cuh).
+// RFB200_PAIR=0 switches back to one line per thread.
+template <int LOGN, int W>
+bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    static const bool on = [] { const char *v = getenv("RFB200_PAIR"); return v ? atoi(v) != 0 : true; }();
+    using Body = PairBody<LOGN, W>;
+    const int64_t e = (int64_t)sizeof(float2);
+    if (!on || dims.empty() || dims[0].is != e || dims[0].os != e || (dims[0].tw && job.twN)) return false;
+    if (job.load_mode != LD_C2C || job.store_mode != ST_C2C || job.flags || (job.n_in && job.n_in != job.n) || job.pre_tab ||
+        job.post_tab || !job.split_out.empty() || job.conv)
+        return false;
+    TileGeom<float> g;
+    const uint64_t ntiles = fill_geom<float>(g, job, dims, (uint32_t)W, true, true);
+    set_prefetch_by_mode<float>(g, job, dims, (uint32_t)W);
+    const float2 *stw = (const float2 *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
+    const size_t smem = (size_t)Body::WP * Body::PITCH * sizeof(float4);
+    auto kern = fft_pow2_pair_kernel<LOGN, W>;
+    static thread_local int dev_set = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_set != dev) {
+        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dev_set = dev;
+    }
+    kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
+    count_launch();
+    RFB_CUDA_CHECK(cudaGetLastError());
+    return true;
 }
 
 // Both steps of a four-step transform of strided lines in one persistent kernel (pow2_fused4_kernel.cuh).

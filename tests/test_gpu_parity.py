@@ -597,3 +597,31 @@ def _fused_fourstep_cases(R, T, dev, rng, n):
     T.c2c(xh, want, [0], True, 1.0)
     check(wide[:, 7 : 7 + 801].cpu().numpy(), want, np.float32, n, "fused four-step, different pitches")
     assert float(wide[:, :7].abs().max()) == 0.0 and float(wide[:, 808:].abs().max()) == 0.0
+
+
+def test_strided_lines_two_per_thread(R):
+    """float32 lines of 128..1024 points along a strided axis (neighbouring lines adjacent): the kernel that keeps two
+    lines per thread (pow2_pair_kernel.cuh) -- odd and even numbers of lines, partial tiles, extra batch dims on either
+    side, in place, both directions, fct != 1, and as the two steps of the four-step split (n = 16384, 65536)."""
+    T = trusted()
+    rng = np.random.default_rng(13)
+    cases = []
+    for n in (128, 256, 512, 1024):
+        cases += [((n, 37), 0), ((n, 64), 0), ((3, n, 45), 1), ((n, 5, 33), 0), ((2, n, 1), 1), ((n, 2), 0)]
+    cases += [((16384, 41), 0), ((65536, 40), 0), ((2, 4096, 70), 1)]
+    for shape, axis in cases:
+        x = cplx(rng, shape, np.complex64)
+        n = shape[axis]
+        for fwd, fct, inplace in ((True, 1.0, False), (False, 0.25, True)):
+            want = np.empty_like(x)
+            T.c2c(x, want, [axis], fwd, fct)
+            src = x.copy()
+            out = src if inplace else np.zeros_like(x)
+            R.c2c(src, out, [axis], fwd, fct)
+            check(out, want, np.float32, n, ("pair", shape, axis, fwd, inplace))
+    # several axes in one call (every pass after the first works in place on the output)
+    x = cplx(rng, (128, 256, 48), np.complex64)
+    want, got = np.empty_like(x), np.empty_like(x)
+    T.c2c(x, want, [0, 1], True, 1.0)
+    R.c2c(x, got, [0, 1], True, 1.0)
+    check(got, want, np.float32, 128 * 256, "pair, two strided axes")

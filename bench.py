@@ -258,7 +258,8 @@ def main():
         per_launch = [(t_row / max(row_launches, 1), row_bytes, row_kernel, row_launches),
                       (t_col / max(col_launches, 1), col_bytes,
                        "fft_fourstep_fused_kernel<float,7,32> columns (both four-step passes, intermediate in L2)" if col_launches == 1
-                       else "fft_pow2_kernel<float,7,32,0> four-step column pass", col_launches)]
+                       else ("fft_pow2_pair_kernel<7,32> four-step column pass" if int(os.environ.get("RFB200_PAIR", "1"))
+                             else "fft_pow2_kernel<float,7,32,0> four-step column pass"), col_launches)]
         dom = max(per_launch, key=lambda p: p[0])
         achieved = dom[1] / (dom[0] * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of that kernel for ONE image, from the

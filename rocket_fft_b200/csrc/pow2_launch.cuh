@@ -8,6 +8,7 @@
 #include "pow2_dual_kernel.cuh"
 #include "pow2_fused4_kernel.cuh"
 #include "pow2_pair_kernel.cuh"
+#include "pow2_async_kernel.cuh"
 
 namespace rfb {
 
@@ -130,6 +131,27 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
 
 template <int LOGN, int W>
 bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+template <int LOGN, int W>
+bool launch_async_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+
+// Strided float32 lines with adjacent neighbours (line-fast tiles).  RFB200_LFMODE: 0 = one line per thread
+// (pow2_kernel.cuh), 1 = two lines per thread (pow2_pair_kernel.cuh; default), 2 = persistent CTAs with the next tile
+// in flight through cp.async (pow2_async_kernel.cuh; 128- and 256-point lines).  RFB200_PAIR=0 is an alias of mode 0.
+inline int lf_mode() {
+    static const int v = [] {
+        const char *p = getenv("RFB200_PAIR");
+        if (p && atoi(p) == 0) return 0;
+        const char *e = getenv("RFB200_LFMODE");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+inline bool lf_plain_job(const LineJob &job, const std::vector<Dim> &dims) {
+    const int64_t e = (int64_t)sizeof(float2);
+    if (dims.empty() || dims[0].is != e || dims[0].os != e || (dims[0].tw && job.twN)) return false;
+    return job.load_mode == LD_C2C && job.store_mode == ST_C2C && !job.flags && (job.n_in == 0 || job.n_in == job.n) &&
+           !job.pre_tab && !job.post_tab && job.split_out.empty() && !job.conv;
+}
 
 template <typename T, int LOGN>
 bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, int mode,
@@ -177,8 +199,11 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     }
     if constexpr (WL == 0) return false;
     else {
+        if constexpr (sizeof(T) == 4 && (LOGN == 7 || LOGN == 8)) {
+            if (lf_mode() == 2 && load_lf && store_lf && launch_async_inst<LOGN, WL>(job, dims, s)) return true;
+        }
         if constexpr (sizeof(T) == 4 && LOGN >= 7 && LOGN <= 10 && WL >= 2) {
-            if (load_lf && store_lf && launch_pair_inst<LOGN, WL>(job, dims, s)) return true;
+            if (lf_mode() >= 1 && load_lf && store_lf && launch_pair_inst<LOGN, WL>(job, dims, s)) return true;
         }
         launch_pow2_inst<T, LOGN, WL, 0>(job, dims, load_lf, store_lf, s);
         return true;
@@ -186,16 +211,10 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
 }
 
 // Strided float32 lines whose neighbours are adjacent on both sides: two lines per thread (pow2_pair_kernel.cuh).
-// RFB200_PAIR=0 switches back to one line per thread.
 template <int LOGN, int W>
 bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
-    static const bool on = [] { const char *v = getenv("RFB200_PAIR"); return v ? atoi(v) != 0 : true; }();
     using Body = PairBody<LOGN, W>;
-    const int64_t e = (int64_t)sizeof(float2);
-    if (!on || dims.empty() || dims[0].is != e || dims[0].os != e || (dims[0].tw && job.twN)) return false;
-    if (job.load_mode != LD_C2C || job.store_mode != ST_C2C || job.flags || (job.n_in && job.n_in != job.n) || job.pre_tab ||
-        job.post_tab || !job.split_out.empty() || job.conv)
-        return false;
+    if (!lf_plain_job(job, dims)) return false;
     TileGeom<float> g;
     const uint64_t ntiles = fill_geom<float>(g, job, dims, (uint32_t)W, true, true);
     set_prefetch_by_mode<float>(g, job, dims, (uint32_t)W);
@@ -210,6 +229,33 @@ bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
         dev_set = dev;
     }
     kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
+    count_launch();
+    RFB_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// The same jobs on persistent CTAs that stage the next tile with cp.async (pow2_async_kernel.cuh).
+template <int LOGN, int W>
+bool launch_async_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+    using Body = AsyncLfBody<LOGN, W>;
+    if (!lf_plain_job(job, dims)) return false;
+    TileGeom<float> g;
+    const uint64_t ntiles = fill_geom<float>(g, job, dims, (uint32_t)W, true, true);
+    const float2 *stw = (const float2 *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
+    const size_t smem = 2 * (size_t)Body::BUF * sizeof(float2);
+    auto kern = fft_pow2_async_kernel<LOGN, W>;
+    static thread_local int dev_set = -1;
+    static thread_local int sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_set != dev) {
+        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RFB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        dev_set = dev;
+    }
+    static const int per_sm = [] { const char *v = getenv("RFB200_ASYNC_CTAS"); return v ? atoi(v) : 3; }();
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1));
+    kern<<<grid, Body::NT, smem, s>>>(g, stw, (uint32_t)ntiles);
     count_launch();
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;

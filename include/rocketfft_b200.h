@@ -170,6 +170,9 @@ void rfb200_launch_count_reset(void);
 /* DST-II/III with ortho=true: 1 (default) reproduces the reference, which scales element
  * 0 (H:3033-3039, README.md:61-65); 0 scales element N-1 as SciPy does. */
 void rfb200_set_dst_ortho_quirk(int enabled);
+/* Host-side view of the tile order of the fused four-step kernel (pow2_fused4_kernel.cuh; test aid, no GPU needed):
+ * unit `unit` of 2*nstrips -> (step << 32) | strip with step 0 = A, 1 = B; -1 past the end or if lag > nstrips. */
+int64_t rfb200_debug_fuse4_unit(uint32_t unit, uint32_t nstrips, uint32_t lag);
 /* Library version string. */
 const char *rfb200_version(void);
 

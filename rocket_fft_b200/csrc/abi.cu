@@ -10,6 +10,7 @@
 
 #include "../../include/rocketfft_b200.h"
 #include "engine.h"
+#include "tile_kernel.cuh"
 
 using namespace rfb;
 
@@ -436,4 +437,10 @@ RFB_EXPORT void rfb200_use_library_stream(void) { g_user_stream_set = false; }
 RFB_EXPORT uint64_t rfb200_launch_count(void) { return rfb::launch_count(); }
 RFB_EXPORT void rfb200_launch_count_reset(void) { rfb::launch_count_reset(); }
 RFB_EXPORT void rfb200_set_dst_ortho_quirk(int enabled) { rfb::set_dst_ortho_quirk(enabled != 0); }
+RFB_EXPORT int64_t rfb200_debug_fuse4_unit(uint32_t unit, uint32_t nstrips, uint32_t lag) {
+    bool stepB = false;
+    uint32_t strip = 0;
+    if (lag > nstrips || !rfb::fuse4_decode_unit(unit, nstrips, lag, stepB, strip)) return -1;
+    return ((int64_t)(stepB ? 1 : 0) << 32) | (int64_t)strip;
+}
 RFB_EXPORT const char *rfb200_version(void) { return "rocketfft_b200 0.1.0 (sm_100a)"; }

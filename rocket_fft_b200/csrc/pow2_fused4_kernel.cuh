@@ -33,16 +33,11 @@ __global__ void __launch_bounds__(W *(1 << LOGN) / 16, p2_min_blocks<T, W *(1 <<
     // tickets; it works them off in order, and the smallest unfinished ticket never depends on a larger one.)
     __shared__ uint32_t s_item[3], s_ready[3];
     const uint32_t S = c.nstrips, lag = c.lag;
-    const uint32_t total_units = 2 * S;
     // item -> (step, strip, tile); unit order: A(0..lag-1), then pairs A(lag + i), B(i), then the last B's
     auto decode = [&](uint32_t item, bool &stepB, uint32_t &strip, uint32_t &tile) -> bool {
         uint32_t unit;
         fdivmod(item, c.d_tiles, unit, tile);
-        if (unit >= total_units) return false;
-        if (unit < lag) { stepB = false; strip = unit; }
-        else if (unit < lag + 2 * (S - lag)) { const uint32_t v = unit - lag; stepB = (v & 1u) != 0; strip = stepB ? (v >> 1) : lag + (v >> 1); }
-        else { stepB = true; strip = S - lag + (unit - lag - 2 * (S - lag)); }
-        return true;
+        return fuse4_decode_unit(unit, S, lag, stepB, strip);
     };
     // the counter a tile waits for (nullptr: none): B(s) needs all of A(s) written, A(s) needs B(s - ring) to have read the slot
     auto dep_flag = [&](bool stepB, uint32_t strip) -> const uint32_t * {

@@ -85,6 +85,17 @@ struct Fuse4Ctl {
     uint32_t *ctr;           // [0] ticket, [1] error flag, [2 .. 2+S) tiles of A(s) done, [2+S .. 2+2S) tiles of B(s) done
 };
 
+// Ticket order of the fused four-step kernel: unit u of 2*S units -> (step, strip).  A(0) .. A(lag-1), then the pairs
+// A(lag + i), B(i), then the last lag B's.  B(s) depends on A(s); A(s), s >= ring, on B(s - ring).  With ring > lag every
+// unit comes after the units it depends on (checked on the host by tests/test_abi.py through rfb200_debug_fuse4_unit).
+__host__ __device__ inline bool fuse4_decode_unit(uint32_t unit, uint32_t S, uint32_t lag, bool &stepB, uint32_t &strip) {
+    if (unit >= 2 * S) return false;
+    if (unit < lag) { stepB = false; strip = unit; }
+    else if (unit < lag + 2 * (S - lag)) { const uint32_t v = unit - lag; stepB = (v & 1u) != 0; strip = stepB ? (v >> 1) : lag + (v >> 1); }
+    else { stepB = true; strip = S - lag + (unit - lag - 2 * (S - lag)); }
+    return true;
+}
+
 // The CTAs resident on an SM tend to load, compute and store in step, which leaves HBM idle while they compute.
 // One thread asks the L2 to fetch the input of the tile that will run pf_dist tiles from now (one bulk-prefetch
 // instruction for the whole tile): DRAM streams in the background and the later CTA's loads hit L2.

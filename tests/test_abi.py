@@ -64,3 +64,33 @@ def test_argument_validation_is_host_side():
         r.r2c(x, x, [0], True, 1.0)
     with pytest.raises(ValueError):
         r.dct(np.zeros(8), np.zeros(8), [0], 5, 1.0, False)
+
+
+def test_fused_fourstep_ticket_order_never_puts_a_consumer_first():
+    """Scheduling invariant of the fused four-step kernel (csrc/pow2_fused4_kernel.cuh), checked on the host through
+    rfb200_debug_fuse4_unit: every (step, strip) appears exactly once, B(s) comes after A(s), and A(s) comes after
+    B(s - ring) for every ring > lag -- a tile that waits can only wait for tickets drawn earlier (no deadlock)."""
+    import ctypes as C
+
+    import rocket_fft_b200 as R
+
+    f = C.CDLL(R.LIB_PATH).rfb200_debug_fuse4_unit
+    f.restype = C.c_int64
+    f.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    for S in (1, 2, 3, 5, 8, 33, 132):
+        for lag in range(1, min(S, 6) + 1):
+            pos = {}
+            for u in range(2 * S):
+                r = f(u, S, lag)
+                assert r >= 0
+                key = (r >> 32, r & 0xFFFFFFFF)
+                assert key not in pos and key[1] < S
+                pos[key] = u
+            assert f(2 * S, S, lag) == -1
+            assert len(pos) == 2 * S
+            for s in range(S):
+                assert pos[(0, s)] < pos[(1, s)]
+                for ring in (lag + 1, lag + 2, lag + 5):
+                    if s >= ring:
+                        assert pos[(1, s - ring)] < pos[(0, s)], (S, lag, ring, s)
+    assert f(0, 2, 3) == -1

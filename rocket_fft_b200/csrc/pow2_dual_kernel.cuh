@@ -24,10 +24,10 @@ namespace rfb {
 
 template <bool B> struct BoolC { static constexpr bool value = B; };
 
-// v * exp(-2 pi i m/64) for 0 <= m <= 16; m is a compile-time constant once the caller's loop is unrolled
+// v * exp(-2 pi i m/64) for 0 <= m < 32; m is a compile-time constant once the caller's loop is unrolled
 __device__ __forceinline__ float2 mul_root64(float2 v, int m) {
+    if (m >= 16) { v = mk<float>(v.y, -v.x); m -= 16; }  // a quarter turn first
     if (m == 0) return v;
-    if (m == 16) return mk<float>(v.y, -v.x);
     float c = 1.f, s = 0.f;
     switch (m) {
         case 1: c = 0.995184727f; s = 0.0980171403f; break;
@@ -52,7 +52,7 @@ __device__ __forceinline__ float2 mul_root64(float2 v, int m) {
 
 // TWC: twiddles of long passes and of the pre/post stages are composed from a few table entries and compile-time
 // roots of unity instead of being loaded one by one (fewer L1 wavefronts, a few more multiplies)
-template <int LOGNH, int MODE, bool TWC = false>  // MODE 1: r2c, MODE 2: c2r (as in pow2_kernel.cuh)
+template <int LOGNH, int MODE, bool TWC = false>  // MODE 0: c2c (2*2^LOGNH points), 1: r2c, 2: c2r (as in pow2_kernel.cuh)
 struct DualBody {
     using T = float;
     using C = float2;
@@ -135,8 +135,8 @@ struct DualBody {
         prefetch_later_tile<T>(g, 1u);
 
         constexpr int R0 = PL::radix(0), NB0 = 16 / R0, ido0 = PL::ido(0);
-        if (MODE == 1) {
-            // x[4e .. 4e+3] = z[2e], z[2e+1] = element e of A and of B
+        if (MODE == 1 || MODE == 0) {
+            // x[4e .. 4e+3] = z[2e], z[2e+1] = element e of A and of B  (MODE 0: z is the complex line itself)
             const float4 *p = reinterpret_cast<const float4 *>(g.in + in_base) + t;
 #pragma unroll
             for (int j = 0; j < NB0; ++j)
@@ -146,6 +146,10 @@ struct DualBody {
                     a[j * R0 + m] = mk<T>(u.x, u.y);
                     b[j * R0 + m] = mk<T>(u.z, u.w);
                 }
+            if (MODE == 0 && g.backward) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { a[i] = cswap(a[i]); b[i] = cswap(b[i]); }
+            }
         } else {
             // Hermitian fold (see MODE 2 of pow2_kernel.cuh): Z[e] = s + i d conj(c_e) with s = X[e] + conj X[N-e],
             // d = X[e] - conj X[N-e], c_e = exp(-2 pi i e/(2N)); c_{e+N/2} = -i c_e.  Im X[0], Im X[N] are ignored
@@ -194,6 +198,25 @@ struct DualBody {
 
         // ---- thread t now holds bins t + j*TPL + q*NH/RL of both transforms ------------------------------------
         constexpr int RL = PL::radix(PL::NPASS - 1), NBL = 16 / RL;
+        if (MODE == 0) {
+            // c2c: the radix-2 combination in registers, Z[k] = A[k] + w^k B[k], Z[k + N/2] = A[k] - w^k B[k];
+            // w^k = w^t exp(-2 pi i q/32) for k = t + q*TPL (TPL = N/32): one table entry and compile-time roots
+            static_assert(NBL == 1, "the last pass is radix 16");
+            C *o = reinterpret_cast<C *>(g.out + out_base) + t;
+            const C wt = __ldg(g.twA + t);  // exp(-2 pi i t/N)
+            const T f = g.fct;
+            const bool bw = g.backward != 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const C wb = cmul(mul_root64(wt, 2 * q), b[q]);
+                C z0 = mk<T>((a[q].x + wb.x) * f, (a[q].y + wb.y) * f);
+                C z1 = mk<T>((a[q].x - wb.x) * f, (a[q].y - wb.y) * f);
+                if (bw) { z0 = cswap(z0); z1 = cswap(z1); }
+                __stcs(o + q * TPL, z0);
+                __stcs(o + q * TPL + NH, z1);
+            }
+            return;
+        }
         if (MODE == 2) {
             float4 *o = reinterpret_cast<float4 *>(g.out + out_base) + t;
             const T f = g.fct;
@@ -265,7 +288,7 @@ struct DualBody {
 };
 
 template <int LOGNH, int MODE, bool TWC>
-__global__ void __launch_bounds__((1 << LOGNH) / 16, 2) fft_pow2_dual_kernel(const TileGeom<float> g, const float2 *__restrict__ stw) {
+__global__ void __launch_bounds__((1 << LOGNH) / 16, (LOGNH >= 13 ? 1 : 2)) fft_pow2_dual_kernel(const TileGeom<float> g, const float2 *__restrict__ stw) {
     extern __shared__ __align__(16) unsigned char smem_raw_p2d[];
     DualBody<LOGNH, MODE, TWC>::run(g, stw, reinterpret_cast<float4 *>(smem_raw_p2d));
 }

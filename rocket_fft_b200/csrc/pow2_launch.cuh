@@ -26,7 +26,15 @@ bool launch_dual_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
     using Body = DualBody<LOGNH, MODE, TWC>;
     // contiguous, fully present lines whose 16-byte {z[2e], z[2e+1]} / {y[2m], y[2m+1]} groups are aligned
     if (job.n_in != 0 && job.n_in != job.n) return false;
-    if (MODE == 1) {
+    if (MODE == 0) {
+        // contiguous complex lines, plain load/store, 16-byte aligned on both sides
+        const int64_t e = (int64_t)sizeof(float2);
+        if (job.is != e || job.os != e || job.load_mode != LD_C2C || job.store_mode != ST_C2C || job.flags || job.twN ||
+            job.pre_tab || job.post_tab || !job.split_out.empty() || job.conv)
+            return false;
+        if (((uint64_t)(uintptr_t)job.in % 16) != 0 || ((uint64_t)(uintptr_t)job.out % 16) != 0) return false;
+        for (auto &d : dims) if (d.is % 16 || d.os % 16) return false;
+    } else if (MODE == 1) {
         if (job.is != (int64_t)sizeof(float) || ((uint64_t)(uintptr_t)job.in % 16) != 0) return false;
         for (auto &d : dims) if (d.is % 16) return false;
     } else {
@@ -35,11 +43,12 @@ bool launch_dual_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
     }
     TileGeom<float> g;
     LineJob j2 = job;
-    j2.n = job.n / 2;  // geometry in complex points
+    if (MODE != 0) j2.n = job.n / 2;  // geometry in complex points
     const uint64_t ntiles = fill_geom<float>(g, j2, dims, 1u, false, false);
-    g.n_out = (uint32_t)(job.n / 2 + 1);
+    if (MODE != 0) g.n_out = (uint32_t)(job.n / 2 + 1);
     g.twA = (const float2 *)get_table(TAB_LINE, job.prec, job.n, 0);
-    if (MODE == 1) {
+    if (MODE == 0) set_prefetch<float>(g, job, dims, 1u, sizeof(float2), job.n);
+    else if (MODE == 1) {
         g.n_in = (uint32_t)job.n;
         set_prefetch<float>(g, job, dims, 1u, sizeof(float), job.n);
     } else set_prefetch<float>(g, job, dims, 1u, sizeof(float2), job.n / 2 + 1);
@@ -194,6 +203,11 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
         }
     }
     if (!lf) {
+        if constexpr (sizeof(T) == 4 && (LOGN == 13 || LOGN == 14)) {
+            // long contiguous complex lines: two interleaved half-length transforms per thread (RFB200_DUAL_C2C=0: off)
+            static const int dc = [] { const char *v = getenv("RFB200_DUAL_C2C"); return v ? atoi(v) : (LOGN == 13 ? 1 : 0); }();
+            if (dc && dual_variant() != 0 && launch_dual_inst<LOGN - 1, 0, true>(job, dims, s)) return true;
+        }
         launch_pow2_inst<T, LOGN, WE, 0>(job, dims, load_lf, store_lf, s);
         return true;
     }

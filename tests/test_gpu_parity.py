@@ -625,3 +625,41 @@ def test_strided_lines_two_per_thread(R):
     T.c2c(x, want, [0, 1], True, 1.0)
     R.c2c(x, got, [0, 1], True, 1.0)
     check(got, want, np.float32, 128 * 256, "pair, two strided axes")
+
+
+def test_long_complex_lines_two_transforms_per_thread(R):
+    """8192- and 16384-point complex64 contiguous lines (the c2c mode of pow2_dual_kernel.cuh when enabled for the
+    length, the single-transform kernel otherwise / for views that are only 8-byte aligned): both directions, in place,
+    padded rows, fct != 1 -- against the reference."""
+    import torch
+
+    T = trusted()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(14)
+    for n in (8192, 16384):
+        base_h = cplx(rng, (5, n + 6), np.complex64)
+        base = torch.from_numpy(base_h).to(dev)
+        for view in (base[:, :n], base[:, 2 : n + 2], base[:, 1 : n + 1], base[3, :n]):
+            xh = np.ascontiguousarray(view.cpu().numpy())
+            for fwd, fct, inplace in ((True, 1.0, False), (False, 1.0 / n, False), (True, 0.5, True)):
+                want = np.empty_like(xh)
+                T.c2c(xh, want, [xh.ndim - 1], fwd, fct)
+                if inplace:
+                    # the same view of a fresh copy of the padded array, transformed in place
+                    full = base.clone()
+                    off = (view.data_ptr() - base.data_ptr()) // 8
+                    src = torch.as_strided(full, view.shape, view.stride(), off)
+                    R.c2c(src, src, [src.dim() - 1], fwd, fct)
+                    got = src
+                else:
+                    src = view
+                    got = torch.empty(view.shape, dtype=torch.complex64, device=dev)
+                    R.c2c(src, got, [src.dim() - 1], fwd, fct)
+                torch.cuda.synchronize()
+                check(got.cpu().numpy(), want, np.float32, n, ("c2c long", n, tuple(view.stride()), fwd, inplace))
+    x = torch.from_numpy(cplx(rng, (2000, 8192), np.complex64)).to(dev)
+    y = torch.empty_like(x)
+    R.c2c(x, y, [1], True, 1.0)
+    ref = torch.fft.fft(x, dim=1)
+    err = float(torch.linalg.vector_norm((y - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
+    assert err < parity.tol(np.float32, 8192), err

@@ -272,6 +272,26 @@ def ihfft(x, n=None, axis=-1, norm=None):
     return _r2cn(x, None if n is None else [n], [axis], norm, False, False)
 
 
+def hfft2(x, s=None, axes=(-2, -1), norm=None):
+    """scipy.fft.hfft2 (O:1516-1528): c2r over the given axes with the forward sign."""
+    return _c2rn(x, s, axes, norm, True, True)
+
+
+def ihfft2(x, s=None, axes=(-2, -1), norm=None):
+    """scipy.fft.ihfft2 (O:1530-1542): r2c over the given axes with the backward sign."""
+    return _r2cn(x, s, axes, norm, False, True)
+
+
+def hfftn(x, s=None, axes=None, norm=None):
+    """scipy.fft.hfftn (O:1544-1556)."""
+    return _c2rn(x, s, axes, norm, True, True)
+
+
+def ihfftn(x, s=None, axes=None, norm=None):
+    """scipy.fft.ihfftn (O:1558-1570)."""
+    return _r2cn(x, s, axes, norm, False, True)
+
+
 # ---------------------------------------------------------------------------------------------
 # DCT / DST
 # ---------------------------------------------------------------------------------------------
@@ -346,6 +366,32 @@ def next_fast_len(target, real=False):
     if target < 0:
         raise ValueError("Target cannot be negative.")
     return _ll.good_size(int(target), bool(real))
+
+
+def prev_fast_len(target, real=False):
+    """scipy.fft.prev_fast_len: the largest 11-smooth (complex) or 5-smooth (real) length <= target -- the companion of
+    next_fast_len for trimming data.  (The reference leaves it as a TODO, O:1872-1877; host-only integer code, same
+    factor sets as good_size, H:589-650.)  target == 0 returns 0 like SciPy; negative targets raise."""
+    target = int(target)
+    if target < 0:
+        raise ValueError("Target length must be positive")
+    if target <= (6 if real else 12):
+        return target
+    primes = (2, 3, 5) if real else (2, 3, 5, 7, 11)
+    best = 1
+
+    def search(i, prod):
+        nonlocal best
+        if i == len(primes):
+            best = max(best, prod)
+            return
+        p = primes[i]
+        while prod <= target:
+            search(i + 1, prod)
+            prod *= p
+
+    search(0, 1)
+    return best
 
 
 # ---------------------------------------------------------------------------------------------

@@ -67,3 +67,26 @@ def test_frequencies_and_fast_lengths():
             assert F.next_fast_len(t, real) == scipy.fft.next_fast_len(t, real), (t, real)
     with pytest.raises(ValueError):
         F.next_fast_len(-1)
+
+
+def test_prev_fast_len_matches_scipy():
+    """prev_fast_len is host-only integer code: bit-exact against scipy.fft.prev_fast_len (SciPy >= 1.14)."""
+    import random
+
+    import scipy.fft
+
+    from rocket_fft_b200 import fft as F
+
+    if not hasattr(scipy.fft, "prev_fast_len"):
+        pytest.skip("scipy.fft.prev_fast_len not available")
+    random.seed(3)
+    targets = list(range(0, 4100)) + [random.randrange(1, 10**8) for _ in range(2000)] + [2**31 - 1, 2**31 + 1, 2**40 + 1]
+    for t in targets:
+        for real in (False, True):
+            assert F.prev_fast_len(t, real) == scipy.fft.prev_fast_len(t, real), (t, real)
+    with pytest.raises(ValueError):
+        F.prev_fast_len(-1)
+    # never above the target, never below the previous power of two, consistent with next_fast_len
+    for t in (13, 1000003, 15015):
+        p = F.prev_fast_len(t)
+        assert p <= t and F.next_fast_len(p) == p

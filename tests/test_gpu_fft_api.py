@@ -190,3 +190,22 @@ def test_shift_roll_and_frequencies(F):
     assert F.fftfreq(8, device="cuda").is_cuda
     with pytest.raises(ValueError):
         F.fftfreq(0)
+
+
+def test_multi_axis_hermitian_family(F):
+    """scipy.fft.hfft2 / ihfft2 / hfftn / ihfftn (reference: rocket_fft/overloads.py:1516-1570): norm x s x axes."""
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((5, 12, 9)) + 1j * rng.standard_normal((5, 12, 9))
+    xr = rng.standard_normal((5, 12, 16))
+    for norm in NORMS:
+        for s, axes in ((None, (-2, -1)), ((10, 14), (-2, -1)), ((7, 9), (0, 2)), ((16, 6), (1, 0))):
+            close(F.hfft2(x, s, axes, norm), scipy.fft.hfft2(x, s, axes, norm=norm))
+            close(F.ihfft2(xr, s, axes, norm), scipy.fft.ihfft2(xr, s, axes, norm=norm))
+        for s, axes in ((None, None), ((4, 12, 14), None), ((6, 11), (0, 1)), (None, (2, 0, 1))):
+            close(F.hfftn(x, s, axes, norm), scipy.fft.hfftn(x, s, axes, norm=norm))
+            close(F.ihfftn(xr, s, axes, norm), scipy.fft.ihfftn(xr, s, axes, norm=norm))
+    # single precision stays single
+    x32 = x.astype(np.complex64)
+    out = F.hfftn(x32)
+    assert out.dtype == np.float32
+    close(out, scipy.fft.hfftn(x32), 1e-5)

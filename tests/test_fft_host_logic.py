@@ -90,3 +90,84 @@ def test_prev_fast_len_matches_scipy():
     for t in (13, 1000003, 15015):
         p = F.prev_fast_len(t)
         assert p <= t and F.next_fast_len(p) == p
+
+
+class _ReferenceBackend:
+    """The low-level calls of fft.py served by the compiled, unmodified reference (oracle/_ref) instead of the CUDA
+    library: lets the whole numpy/scipy-style host layer (padding, cropping, norm factors, axis handling, dtype
+    promotion, type inversion) be checked against SciPy on a machine without a GPU."""
+
+    def __init__(self, ref):
+        self.ref = ref
+
+    def c2c(self, a, o, axes, fwd, fct):
+        return self.ref.c2c(a, o, list(axes), fwd, fct, 1)
+
+    def c2c_sym(self, a, o, axes, fwd, fct):
+        return self.ref.c2c_sym(a, o, list(axes), fwd, fct, 1)
+
+    def r2c(self, a, o, axes, fwd, fct):
+        return self.ref.r2c(a, o, list(axes), fwd, fct, 1)
+
+    def c2r(self, a, o, axes, fwd, fct):
+        return self.ref.c2r(a, o, list(axes), fwd, fct, 1)
+
+    def dct(self, a, o, axes, type, fct, ortho):
+        return self.ref.dct(a, o, list(axes), type, fct, ortho, 1)
+
+    def dst(self, a, o, axes, type, fct, ortho):
+        return self.ref.dst(a, o, list(axes), type, fct, ortho, 1)
+
+
+def test_host_layer_on_top_of_the_reference_library_matches_scipy(monkeypatch):
+    import parity
+
+    ref = parity.reflib()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    monkeypatch.setattr(F, "_ll", _ReferenceBackend(ref))
+
+    def close(a, b, tol=1e-11):
+        assert a.shape == b.shape, (a.shape, b.shape)
+        assert parity.l2err(a, b) < tol
+
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((5, 12, 9)) + 1j * rng.standard_normal((5, 12, 9))
+    xr = rng.standard_normal((5, 12, 16))
+    for norm in (None, "backward", "ortho", "forward"):
+        for n in (None, 7, 12, 20):
+            for axis in (-1, 0, 1):
+                close(F.fft(x, n, axis, norm), scipy.fft.fft(x, n, axis, norm))
+                close(F.ifft(x, n, axis, norm), scipy.fft.ifft(x, n, axis, norm))
+                close(F.fft(xr, n, axis, norm), scipy.fft.fft(xr, n, axis, norm))
+                close(F.rfft(xr, n, axis, norm), scipy.fft.rfft(xr, n, axis, norm))
+                close(F.irfft(x, n, axis, norm), scipy.fft.irfft(x, n, axis, norm))
+                close(F.hfft(x, n, axis, norm), scipy.fft.hfft(x, n, axis, norm))
+                close(F.ihfft(xr, n, axis, norm), scipy.fft.ihfft(xr, n, axis, norm))
+        for s, axes in ((None, (-2, -1)), ((10, 14), (-2, -1)), ((7, 9), (0, 2)), ((16, 6), (1, 0))):
+            close(F.fft2(x, s, axes, norm), scipy.fft.fft2(x, s, axes, norm=norm))
+            close(F.ifft2(x, s, axes, norm), scipy.fft.ifft2(x, s, axes, norm=norm))
+            close(F.rfft2(xr, s, axes, norm), scipy.fft.rfft2(xr, s, axes, norm=norm))
+            close(F.irfft2(x, s, axes, norm), scipy.fft.irfft2(x, s, axes, norm=norm))
+            close(F.hfft2(x, s, axes, norm), scipy.fft.hfft2(x, s, axes, norm=norm))
+            close(F.ihfft2(xr, s, axes, norm), scipy.fft.ihfft2(xr, s, axes, norm=norm))
+        for s, axes in ((None, None), ((4, 12, 14), None), ((6, 11), (0, 1)), (None, (2, 0, 1))):
+            close(F.fftn(x, s, axes, norm), scipy.fft.fftn(x, s, axes, norm=norm))
+            close(F.ifftn(x, s, axes, norm), scipy.fft.ifftn(x, s, axes, norm=norm))
+            close(F.rfftn(xr, s, axes, norm), scipy.fft.rfftn(xr, s, axes, norm=norm))
+            close(F.irfftn(x, s, axes, norm), scipy.fft.irfftn(x, s, axes, norm=norm))
+            close(F.hfftn(x, s, axes, norm), scipy.fft.hfftn(x, s, axes, norm=norm))
+            close(F.ihfftn(xr, s, axes, norm), scipy.fft.ihfftn(xr, s, axes, norm=norm))
+        for type in (1, 2, 3, 4):
+            for n in (None, 9, 20):
+                close(F.dct(xr, type, n, 1, norm), scipy.fft.dct(xr, type, n, 1, norm))
+                close(F.idct(xr, type, n, 1, norm), scipy.fft.idct(xr, type, n, 1, norm))
+            close(F.dctn(xr, type, None, (0, 2), norm), scipy.fft.dctn(xr, type, None, (0, 2), norm))
+            close(F.idctn(xr, type, (6, 10), (0, 1), norm), scipy.fft.idctn(xr, type, (6, 10), (0, 1), norm))
+        # DST: the default norm only, as in the reference's own comparison grid (tests/test_scipy_compare.py:365-367)
+    for type in (1, 2, 3, 4):
+        close(F.dst(xr, type, None, 1), scipy.fft.dst(xr, type, None, 1))
+        close(F.idst(xr, type, 9, 0), scipy.fft.idst(xr, type, 9, 0))
+        close(F.dstn(xr, type, None, (0, 2)), scipy.fft.dstn(xr, type, None, (0, 2)))
+        close(F.idstn(xr, type, (6, 10), (0, 1)), scipy.fft.idstn(xr, type, (6, 10), (0, 1)))
+    assert F.hfftn(x.astype(np.complex64)).dtype == np.float32

@@ -324,6 +324,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            # the BASELINE label's "5N*log2N" applied verbatim to real data is exactly twice `value`
+            "value_5NlogN_label": 2.0 * value,
             "clocks": clocks, "stages": stages, "library": R.version()}
     print(json.dumps(line))
     if world > 1:

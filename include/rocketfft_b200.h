@@ -173,6 +173,11 @@ void rfb200_set_dst_ortho_quirk(int enabled);
 /* Host-side view of the tile order of the fused four-step kernel (pow2_fused4_kernel.cuh; test aid, no GPU needed):
  * unit `unit` of 2*nstrips -> (step << 32) | strip with step 0 = A, 1 = B; -1 past the end or if lag > nstrips. */
 int64_t rfb200_debug_fuse4_unit(uint32_t unit, uint32_t nstrips, uint32_t lag);
+/* Measurement aid (csrc/probe.cu, tools/probe_strided_copy.py): a pure copy with the access pattern of the four-step column
+ * passes over a rows x cols complex64 array of row pitch `pitch_bytes` (rows a multiple of 128): mode 0 strided -> strided,
+ * 1 strided -> dense (out needs ceil(cols/32)*rows*256 bytes), 2 dense -> strided.  Returns 0 on success. */
+int rfb200_debug_tile_copy(const void *in, void *out, uint64_t rows, uint64_t cols, int64_t pitch_bytes, int mode,
+                           void *stream);
 /* Library version string. */
 const char *rfb200_version(void);
 

@@ -236,7 +236,14 @@ bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
     set_prefetch_by_mode<float>(g, job, dims, (uint32_t)W);
     const float2 *stw = (const float2 *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
     const size_t smem = (size_t)Body::WP * Body::PITCH * sizeof(float4);
-    auto kern = fft_pow2_pair_kernel<LOGN, W>;
+    // RFB200_LF_CTAS = 5 / 6: the 128-point instantiation compiled for more resident CTAs per SM (not yet measured;
+    // default: 4, the measured configuration)
+    static const int ctas = [] { const char *v = getenv("RFB200_LF_CTAS"); return v ? atoi(v) : 4; }();
+    void (*kern)(const TileGeom<float>, const float2 *) = fft_pow2_pair_kernel<LOGN, W>;
+    if constexpr (LOGN == 7) {
+        if (ctas == 5) kern = fft_pow2_pair_kernel_occ<LOGN, W, 5>;
+        else if (ctas >= 6) kern = fft_pow2_pair_kernel_occ<LOGN, W, 6>;
+    }
     static thread_local int dev_set = -1;
     int dev = 0;
     cudaGetDevice(&dev);

@@ -325,17 +325,6 @@ static dim3 ew_grid(uint64_t n_e, uint64_t L) {
     return dim3((unsigned)((n_e + 255) / 256), (unsigned)std::min<uint64_t>(L, 32768), 1);
 }
 
-static std::vector<Dim> contiguous_batch(const std::vector<Dim> &b, uint64_t line_bytes, bool as_input) {
-    // same extents, C-order contiguous strides on the scratch side
-    std::vector<Dim> r = b;
-    int64_t acc = (int64_t)line_bytes;
-    for (size_t i = 0; i < r.size(); ++i) {  // dim 0 fastest in BatchIdx order
-        if (as_input) r[i].is = acc; else r[i].os = acc;
-        acc *= r[i].n;
-    }
-    return r;
-}
-
 // ---------------------------------------------------------------------------------------
 // the three algorithms
 // ---------------------------------------------------------------------------------------

@@ -48,7 +48,9 @@ def test_good_size_bit_exact_vs_golden_and_reference():
     ref = parity.reflib()
     if ref is not None:
         rng = np.random.default_rng(0)
-        targets = list(range(0, 100000, 7)) + [int(x) for x in rng.integers(1, 2**40, 300)]
+        # every target up to 10^6 and the large probes of SURVEY.md appendix B
+        targets = list(range(0, 1000001)) + [2**31 - 1, 2**31 + 1, 2**40 + 1, 1000003, 2000005, 15015]
+        targets += [int(x) for x in rng.integers(1, 2**40, 300)]
         for t in targets:
             assert r.good_size(t, False) == ref.good_size(t, False)
             assert r.good_size(t, True) == ref.good_size(t, True)

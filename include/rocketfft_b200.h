@@ -178,6 +178,11 @@ int64_t rfb200_debug_fuse4_unit(uint32_t unit, uint32_t nstrips, uint32_t lag);
  * 1 strided -> dense (out needs ceil(cols/32)*rows*256 bytes), 2 dense -> strided.  Returns 0 on success. */
 int rfb200_debug_tile_copy(const void *in, void *out, uint64_t rows, uint64_t cols, int64_t pitch_bytes, int mode,
                            void *stream);
+/* The same aid in general form: tiles0 x tiles1 CTAs of `threads` threads, each copying nrows segments of seg_bytes (in place
+ * coordinates: segment r of tile (a, b) at a*seg_bytes + b*outer_stride + r*row_stride); at most 16 items of 8 bytes per thread;
+ * smem_bytes of (unused) dynamic shared memory per CTA reproduce a transform kernel's occupancy. */
+int rfb200_debug_seg_copy(const void *in, void *out, uint32_t nrows, uint32_t seg_bytes, int64_t row_stride, uint32_t tiles0,
+                          uint32_t tiles1, int64_t outer_stride, uint32_t threads, uint32_t smem_bytes, void *stream);
 /* Library version string. */
 const char *rfb200_version(void);
 

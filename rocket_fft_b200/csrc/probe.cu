@@ -35,7 +35,43 @@ __global__ void __launch_bounds__(256, 4) tile_copy_kernel(const char *__restric
     }
 }
 
+// General form: every CTA copies `nrows` segments of `seg` bytes (8-byte items, all loads issued before the first store);
+// segment r of tile (a, b) lies at  a*seg + b*outer + r*row_stride  (a < tiles0).
+template <int PER>
+__global__ void __launch_bounds__(1024) seg_copy_kernel(const char *__restrict__ in, char *__restrict__ out, uint32_t nrows, uint32_t seg8,
+                                                      int64_t row_stride, uint32_t tiles0, int64_t outer) {
+    const uint32_t a = blockIdx.x % tiles0, b = blockIdx.x / tiles0;
+    const int64_t base = (int64_t)a * seg8 * 8 + (int64_t)b * outer;
+    const uint32_t total = nrows * seg8;
+    float2 v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t idx = threadIdx.x + (uint32_t)i * blockDim.x;
+        if (idx < total) v[i] = *reinterpret_cast<const float2 *>(in + base + (int64_t)(idx / seg8) * row_stride + (int64_t)(idx % seg8) * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t idx = threadIdx.x + (uint32_t)i * blockDim.x;
+        if (idx < total) *reinterpret_cast<float2 *>(out + base + (int64_t)(idx / seg8) * row_stride + (int64_t)(idx % seg8) * 8) = v[i];
+    }
+}
+
 }  // namespace
+
+extern "C" __attribute__((visibility("default"))) int rfb200_debug_seg_copy(const void *in, void *out, uint32_t nrows, uint32_t seg_bytes,
+                                                                            int64_t row_stride, uint32_t tiles0, uint32_t tiles1,
+                                                                            int64_t outer_stride, uint32_t threads, uint32_t smem_bytes,
+                                                                            void *stream) {
+    // smem_bytes: dynamic shared memory requested per CTA (unused by the kernel) to reproduce a transform kernel's occupancy
+    if (seg_bytes % 8 || threads == 0 || threads > 1024 || tiles0 == 0 || tiles1 == 0 || smem_bytes > 227 * 1024) return 1;
+    if (cudaFuncSetAttribute(seg_copy_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 2;
+    const uint32_t seg8 = seg_bytes / 8;
+    const uint64_t per = ((uint64_t)nrows * seg8 + threads - 1) / threads;
+    if (per > 16) return 1;
+    seg_copy_kernel<16><<<tiles0 * tiles1, threads, smem_bytes, (cudaStream_t)stream>>>((const char *)in, (char *)out, nrows, seg8, row_stride, tiles0,
+                                                                            outer_stride);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
 
 extern "C" __attribute__((visibility("default"))) int rfb200_debug_tile_copy(const void *in, void *out, uint64_t rows,
                                                                              uint64_t cols, int64_t pitch_bytes, int mode,

@@ -22,8 +22,11 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     return v;
 }
 
-template <typename T, int LOGN, int W>
-__global__ void __launch_bounds__(W *(1 << LOGN) / 16, p2_min_blocks<T, W *(1 << LOGN) / 16>())
+// MINB: resident CTAs per SM the kernel is compiled for (0: the register kernel's own target).  More CTAs mean fewer
+// registers per thread and a few spilled values, but the tile body is latency-bound and the
+// fused form has DRAM headroom to use.
+template <typename T, int LOGN, int W, int MINB = 0>
+__global__ void __launch_bounds__(W *(1 << LOGN) / 16, MINB ? MINB : p2_min_blocks<T, W *(1 << LOGN) / 16>())
     fft_fourstep_fused_kernel(const TileGeom<T> gA, const TileGeom<T> gB, const cx<T> *__restrict__ stw, const Fuse4Ctl c) {
     using Body = Pow2Body<T, LOGN, W, 0>;
     extern __shared__ __align__(16) unsigned char smem_raw_f4[];

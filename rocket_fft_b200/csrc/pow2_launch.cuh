@@ -300,7 +300,12 @@ bool launch_fused4_logn(const LineJob &A, const std::vector<Dim> &dA, const Line
     c.d_ring = make_fastdiv(c.ring);
     const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, A.prec, 1ull << LOGN, 0);
     const size_t smem = (size_t)W * Body::PITCH * sizeof(cx<T>);
-    auto kern = fft_fourstep_fused_kernel<T, LOGN, W>;
+    // RFB200_LF_CTAS = 5 / 6: compiled for more resident CTAs per SM (unmeasured so far; default: the register kernel's 4)
+    static const int ctas = [] { const char *v = getenv("RFB200_LF_CTAS"); return v ? atoi(v) : 0; }();
+    void (*kern)(const TileGeom<T>, const TileGeom<T>, const cx<T> *, const Fuse4Ctl) = fft_fourstep_fused_kernel<T, LOGN, W>;
+    int per_sm = p2_min_blocks<T, Body::NT>();
+    if (ctas == 5) { kern = fft_fourstep_fused_kernel<T, LOGN, W, 5>; per_sm = 5; }
+    else if (ctas >= 6) { kern = fft_fourstep_fused_kernel<T, LOGN, W, 6>; per_sm = 6; }
     static thread_local int dev_set = -1;
     static thread_local int sms = 0;
     int dev = 0;
@@ -311,7 +316,7 @@ bool launch_fused4_logn(const LineJob &A, const std::vector<Dim> &dA, const Line
         dev_set = dev;
     }
     const uint64_t items = 2ull * c.nstrips * c.tiles;
-    const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)sms * p2_min_blocks<T, Body::NT>());
+    const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)sms * (uint64_t)per_sm);
     kern<<<grid, Body::NT, smem, s>>>(gA, gB, stw, c);
     count_launch();
     RFB_CUDA_CHECK(cudaGetLastError());

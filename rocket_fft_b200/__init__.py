@@ -32,4 +32,6 @@ from .lowlevel import (  # noqa: F401
     version,
 )
 
+from .fft import get_workers, numpy_like, scipy_like, set_workers  # noqa: F401,E402  (rocket_fft/__init__.py:3-15)
+
 __version__ = "0.1.0"

@@ -79,6 +79,47 @@ def _is_complex(dt):
 
 
 # ---------------------------------------------------------------------------------------------
+# NumPy / SciPy flavour (reference: rocket_fft/overloads.py:325-357, 380-405, rocket_fft/__init__.py:12-15)
+# ---------------------------------------------------------------------------------------------
+# SciPy rejects duplicate axes in the multi-axis transforms, NumPy accepts them (the axis is then transformed twice).
+# Like the reference the SciPy behaviour is the default when SciPy is installed.
+import importlib.util as _ilu
+
+_unique_axes = _ilu.find_spec("scipy") is not None
+_num_workers = 1
+
+
+def numpy_like():
+    """Duplicate axes are allowed (numpy.fft semantics)."""
+    global _unique_axes
+    _unique_axes = False
+
+
+def scipy_like():
+    """Duplicate axes raise ValueError("All axes must be unique.") (scipy.fft semantics)."""
+    global _unique_axes
+    _unique_axes = True
+
+
+def get_workers():
+    """The reference's worker count (O:345-346).  Accepted for interface compatibility: the parallelism here is the GPU grid."""
+    return _num_workers
+
+
+def set_workers(workers):
+    """Validated like the reference (O:349-356) and otherwise ignored (`nthreads` has no meaning on the GPU)."""
+    import os
+
+    global _num_workers
+    workers = int(workers)
+    if workers < 1:
+        raise ValueError("Number of workers cannot be smaller than one.")
+    if workers > (os.cpu_count() or 1):
+        raise ValueError(f"Number of workers exceeds CPU count of {os.cpu_count() or 1}.")
+    _num_workers = workers
+
+
+# ---------------------------------------------------------------------------------------------
 # argument normalisation
 # ---------------------------------------------------------------------------------------------
 def _shape_axes(x, s, axes, default_all):
@@ -87,6 +128,8 @@ def _shape_axes(x, s, axes, default_all):
         if s is None:
             axes = list(range(nd)) if default_all else [nd - 1]
         else:
+            if len(s if hasattr(s, "__len__") else [s]) > nd:
+                raise ValueError("Shape requires more axes than are present.")
             axes = list(range(nd - len(s), nd))
     else:
         axes = [int(a) for a in (axes if hasattr(axes, "__len__") else [axes])]
@@ -94,6 +137,8 @@ def _shape_axes(x, s, axes, default_all):
     for a in axes:
         if not 0 <= a < nd:
             raise ValueError("axes exceeds dimensionality of input")
+    if _unique_axes and len(set(axes)) != len(axes):
+        raise ValueError("All axes must be unique.")
     if s is None:
         s = [x.shape[a] for a in axes]
     else:

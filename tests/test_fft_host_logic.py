@@ -171,3 +171,36 @@ def test_host_layer_on_top_of_the_reference_library_matches_scipy(monkeypatch):
         close(F.dstn(xr, type, None, (0, 2)), scipy.fft.dstn(xr, type, None, (0, 2)))
         close(F.idstn(xr, type, (6, 10), (0, 1)), scipy.fft.idstn(xr, type, (6, 10), (0, 1)))
     assert F.hfftn(x.astype(np.complex64)).dtype == np.float32
+
+
+def test_numpy_like_and_scipy_like_duplicate_axes_policy(monkeypatch):
+    """rocket_fft.numpy_like() / scipy_like() (O:325-339, 380-405): SciPy rejects duplicate axes, NumPy transforms the
+    axis twice.  Checked on CPU with the compiled reference as the backend."""
+    import parity
+    import rocket_fft_b200 as R
+
+    x = np.arange(24.0).reshape(4, 6) + 1j
+    F.scipy_like()
+    try:
+        with pytest.raises(ValueError, match="unique"):
+            F._shape_axes(x, None, (0, 0), True)
+        with pytest.raises(ValueError, match="unique"):
+            F._shape_axes(x, (4, 4), (1, -1), True)
+        with pytest.raises(ValueError, match="more axes"):
+            F._shape_axes(x, (2, 3, 4), None, True)
+        assert F._shape_axes(x, None, (1, 0), True) == ([6, 4], [1, 0])
+        R.numpy_like()
+        assert F._shape_axes(x, None, (0, 0), True) == ([4, 4], [0, 0])
+        ref = parity.reflib()
+        if ref is not None:
+            monkeypatch.setattr(F, "_ll", _ReferenceBackend(ref))
+            got = F.fft2(x, axes=(0, 0))
+            assert parity.l2err(got, np.fft.fft2(x, axes=(0, 0))) < 1e-12
+    finally:
+        R.scipy_like()
+    assert R.get_workers() == 1
+    R.set_workers(1)
+    with pytest.raises(ValueError):
+        R.set_workers(0)
+    with pytest.raises(ValueError):
+        R.set_workers(10**6)

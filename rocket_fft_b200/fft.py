@@ -119,6 +119,21 @@ def set_workers(workers):
     _num_workers = workers
 
 
+def _scipy_extras(overwrite_x, workers, plan=None):
+    """The scipy.fft keyword arguments that have no meaning here, validated like the reference (O:555-572; `plan` as SciPy):
+    `overwrite_x` is a permission, never a requirement (the result is always a new array); `workers` is checked and ignored."""
+    import os
+
+    if plan is not None:
+        raise NotImplementedError("Passing a precomputed plan is not yet supported by scipy.fft functions")
+    if workers is not None:
+        workers = int(workers)
+        if workers == 0:
+            raise ValueError("Workers must not be zero.")
+        if workers < -(os.cpu_count() or 1):
+            raise ValueError("Workers value out of range.")
+
+
 # ---------------------------------------------------------------------------------------------
 # argument normalisation
 # ---------------------------------------------------------------------------------------------
@@ -260,80 +275,98 @@ def _c2rn(x, s, axes, norm, forward, default_all):
     return out
 
 
-def fft(x, n=None, axis=-1, norm=None):
+def fft(x, n=None, axis=-1, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2cn(x, None if n is None else [n], [axis], norm, True, False)
 
 
-def ifft(x, n=None, axis=-1, norm=None):
+def ifft(x, n=None, axis=-1, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2cn(x, None if n is None else [n], [axis], norm, False, False)
 
 
-def fft2(x, s=None, axes=(-2, -1), norm=None):
+def fft2(x, s=None, axes=(-2, -1), norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2cn(x, s, axes, norm, True, True)
 
 
-def ifft2(x, s=None, axes=(-2, -1), norm=None):
+def ifft2(x, s=None, axes=(-2, -1), norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2cn(x, s, axes, norm, False, True)
 
 
-def fftn(x, s=None, axes=None, norm=None):
+def fftn(x, s=None, axes=None, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2cn(x, s, axes, norm, True, True)
 
 
-def ifftn(x, s=None, axes=None, norm=None):
+def ifftn(x, s=None, axes=None, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2cn(x, s, axes, norm, False, True)
 
 
-def rfft(x, n=None, axis=-1, norm=None):
+def rfft(x, n=None, axis=-1, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _r2cn(x, None if n is None else [n], [axis], norm, True, False)
 
 
-def irfft(x, n=None, axis=-1, norm=None):
+def irfft(x, n=None, axis=-1, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2rn(x, None if n is None else [n], [axis], norm, False, False)
 
 
-def rfft2(x, s=None, axes=(-2, -1), norm=None):
+def rfft2(x, s=None, axes=(-2, -1), norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _r2cn(x, s, axes, norm, True, True)
 
 
-def irfft2(x, s=None, axes=(-2, -1), norm=None):
+def irfft2(x, s=None, axes=(-2, -1), norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2rn(x, s, axes, norm, False, True)
 
 
-def rfftn(x, s=None, axes=None, norm=None):
+def rfftn(x, s=None, axes=None, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _r2cn(x, s, axes, norm, True, True)
 
 
-def irfftn(x, s=None, axes=None, norm=None):
+def irfftn(x, s=None, axes=None, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2rn(x, s, axes, norm, False, True)
 
 
-def hfft(x, n=None, axis=-1, norm=None):
+def hfft(x, n=None, axis=-1, norm=None, overwrite_x=False, workers=None, *, plan=None):
     """FFT of a Hermitian-symmetric signal (real spectrum): c2r with the forward sign."""
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2rn(x, None if n is None else [n], [axis], norm, True, False)
 
 
-def ihfft(x, n=None, axis=-1, norm=None):
+def ihfft(x, n=None, axis=-1, norm=None, overwrite_x=False, workers=None, *, plan=None):
+    _scipy_extras(overwrite_x, workers, plan)
     return _r2cn(x, None if n is None else [n], [axis], norm, False, False)
 
 
-def hfft2(x, s=None, axes=(-2, -1), norm=None):
+def hfft2(x, s=None, axes=(-2, -1), norm=None, overwrite_x=False, workers=None, *, plan=None):
     """scipy.fft.hfft2 (O:1516-1528): c2r over the given axes with the forward sign."""
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2rn(x, s, axes, norm, True, True)
 
 
-def ihfft2(x, s=None, axes=(-2, -1), norm=None):
+def ihfft2(x, s=None, axes=(-2, -1), norm=None, overwrite_x=False, workers=None, *, plan=None):
     """scipy.fft.ihfft2 (O:1530-1542): r2c over the given axes with the backward sign."""
+    _scipy_extras(overwrite_x, workers, plan)
     return _r2cn(x, s, axes, norm, False, True)
 
 
-def hfftn(x, s=None, axes=None, norm=None):
+def hfftn(x, s=None, axes=None, norm=None, overwrite_x=False, workers=None, *, plan=None):
     """scipy.fft.hfftn (O:1544-1556)."""
+    _scipy_extras(overwrite_x, workers, plan)
     return _c2rn(x, s, axes, norm, True, True)
 
 
-def ihfftn(x, s=None, axes=None, norm=None):
+def ihfftn(x, s=None, axes=None, norm=None, overwrite_x=False, workers=None, *, plan=None):
     """scipy.fft.ihfftn (O:1558-1570)."""
+    _scipy_extras(overwrite_x, workers, plan)
     return _r2cn(x, s, axes, norm, False, True)
 
 
@@ -374,35 +407,43 @@ def _r2rn(x, type, s, axes, norm, orthogonalize, forward, cosine, default_all):
     return out
 
 
-def dct(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+def dct(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, True, True, False)
 
 
-def idct(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+def idct(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, False, True, False)
 
 
-def dst(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+def dst(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, True, False, False)
 
 
-def idst(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None):
+def idst(x, type=2, n=None, axis=-1, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, None if n is None else [n], [axis], norm, orthogonalize, False, False, False)
 
 
-def dctn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+def dctn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, s, axes, norm, orthogonalize, True, True, True)
 
 
-def idctn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+def idctn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, s, axes, norm, orthogonalize, False, True, True)
 
 
-def dstn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+def dstn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, s, axes, norm, orthogonalize, True, False, True)
 
 
-def idstn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None):
+def idstn(x, type=2, s=None, axes=None, norm=None, orthogonalize=None, *, overwrite_x=False, workers=None):
+    _scipy_extras(overwrite_x, workers)
     return _r2rn(x, type, s, axes, norm, orthogonalize, False, False, True)
 
 

@@ -204,3 +204,25 @@ def test_numpy_like_and_scipy_like_duplicate_axes_policy(monkeypatch):
         R.set_workers(0)
     with pytest.raises(ValueError):
         R.set_workers(10**6)
+
+
+def test_scipy_keyword_arguments_are_accepted_and_validated(monkeypatch):
+    """overwrite_x / workers / plan of the scipy.fft signatures (validated like O:555-572, otherwise without effect)."""
+    import parity
+
+    ref = parity.reflib()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    monkeypatch.setattr(F, "_ll", _ReferenceBackend(ref))
+    x = np.arange(12.0).reshape(3, 4)
+    keep = x.copy()
+    a = F.fft(x, None, -1, None, True, 2)            # positional like scipy.fft.fft(x, n, axis, norm, overwrite_x, workers)
+    assert parity.l2err(a, scipy.fft.fft(x)) < 1e-12 and np.array_equal(x, keep)
+    assert parity.l2err(F.rfft2(x, workers=-1, overwrite_x=True), scipy.fft.rfft2(x)) < 1e-12
+    assert parity.l2err(F.dctn(x, 2, workers=1, overwrite_x=False), scipy.fft.dctn(x, 2)) < 1e-12
+    with pytest.raises(ValueError, match="zero"):
+        F.ifft(x, workers=0)
+    with pytest.raises(ValueError, match="range"):
+        F.fftn(x, workers=-(10**6))
+    with pytest.raises(NotImplementedError):
+        F.fft(x, plan=object())

@@ -1,20 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the transform path (contract: see DESIGN.md "Measurement").
 
-Workload (BASELINE.json configs[1]): np.fft.rfft2 of float32 16384x16384 images through
-the low-level r2c(axes=[1,2]) call, IMAGES images per GPU, batch-sharded over N GPUs with no
-data-path collective (weak scaling).  A step = one rfft2 pass over the rank's images.
+Workload (BASELINE.json configs[1]): np.fft.rfft2 of float32 16384x16384 images through the low-level
+r2c(axes=[1,2]) call, --images images per GPU, batch-sharded over N GPUs with no data-path collective
+(weak scaling).  A step = one rfft2 pass over the rank's images.
 
-  value   : GFLOP/s over all ranks, inputs resident in HBM, CUDA-event timed (max over ranks)
-  e2e     : same metric through the numba_r2c C-ABI entry point with pinned HOST buffers
-            (H2D + kernels + D2H inside the timed region)
-  roofline: dominant kernel's algorithmic bytes / its event-timed duration vs MEASURED_PEAKS.json
-  cpu_baseline / --impl reference: the reference's own PocketFFT path (oracle/_ref, built from
-            /root/reference by oracle/Makefile) with all host threads on the same workload.
+  value        GFLOP/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  roofline     the step's longest kernel (named from the library's launch trace): algorithmic bytes / its
+               event-timed duration against MEASURED_PEAKS.json
+  parity       the device result of one image against the reference's CPU result of the same input
+  e2e          the same step through the numba_r2c C-ABI entry point with pinned HOST buffers (H2D + kernels +
+               D2H inside the timed region), with the copies alone beside it (h2d_ms, d2h_ms, copy_only_ms)
+               and the same call on plain pageable NumPy arrays (e2e_pageable)
+  fftn         BASELINE.json configs[2]: fftn of a complex64 1024^3 volume on the same N GPUs (N = 1: one
+               c2c call; N > 1: slab decomposition with the FFT + NVLink all-to-all fused in one kernel),
+               total ms, the exchange alone, its bus bandwidth, parity against the reference at 512^3
+  other_configs  (N = 1) the remaining BASELINE configs, device-resident, one line each
+  cpu_baseline / --impl reference: the reference's own PocketFFT path (oracle/_ref, the UNMODIFIED reference
+               compiled by oracle/Makefile) with all host threads on the same workload.  The reference arm
+               imports nothing of the product: the only shared library it maps is oracle/_ref's.
 
-flops convention: 2.5*N*log2(N) per real N-point image (the standard real-FFT count; the
-BASELINE label "5N*log2N" applied verbatim to real data is exactly 2x this -- both arms use
-the same formula so ratios are unaffected).
+flops convention: 2.5*N*log2(N) per real N-point image (the standard real-FFT count; the BASELINE label
+"5N*log2N" applied verbatim to real data is exactly 2x this -- both arms use the same formula).
 """
 import argparse
 import json
@@ -30,6 +37,7 @@ sys.path.insert(0, ROOT)
 
 H = W = 16384
 WORKLOAD = "cfg2: rfft2 float32 16384x16384 (r2c axes=[1,2]), batch-sharded images"
+METRIC = "rfft2 GFLOP/s (2.5*N*log2N per real image)"
 
 
 def flops_per_image():
@@ -39,6 +47,13 @@ def flops_per_image():
 
 def alg_bytes_per_image():
     return H * W * 4 + H * (W // 2 + 1) * 8
+
+
+def make_config(args, world):
+    return {"workload": WORKLOAD, "images_per_gpu": args.images, "image": [H, W], "axes": [1, 2],
+            "flops_per_image": flops_per_image(), "algorithmic_bytes_per_image": alg_bytes_per_image(),
+            "l2_policy": "inputs (1 GiB per image) are far larger than the 126 MB L2; no flush needed",
+            "parallelism": f"batch-sharded x{world} (no collective)"}
 
 
 class ClockSampler:
@@ -97,44 +112,70 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_rfft2(steps, warmup, sample_rows=None):
-    """Times the reference's own CPU implementation (oracle/_ref) -- or, if that library did
-    not travel, the NumPy oracle -- on the same workload with all host threads."""
+# ---------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle/_ref; the NumPy restatement if that library did not travel)
+# ---------------------------------------------------------------------------------------------------
+def reference_lib():
+    """(callable r2c(x, out, axes, forward, fct, nthreads), c2c likewise, kind, cores) -- no product imports."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libpocketfft_ref.so")
+    cores = os.cpu_count() or 1
+    if os.path.exists(so):
+        from oracle.abi_view import RefLib
+
+        return RefLib(so), "reference", cores
+    from oracle import pocketfft_oracle as O
+
+    class Port:
+        def r2c(self, a, b, axes, fwd, fct, nthreads=1):
+            return O.r2c(a, b, axes, fwd, fct)
+
+        def c2c(self, a, b, axes, fwd, fct, nthreads=1):
+            return O.c2c(a, b, axes, fwd, fct)
+
+    return Port(), "port", 1
+
+
+def cpu_reference_rfft2(images, steps, warmup):
+    """Times the reference on `images` float32 16384x16384 images per step (r2c axes=[1,2], nthreads = all cores)."""
     import numpy as np
 
-    cores = os.cpu_count() or 1
-    so = os.path.join(ROOT, "oracle", "_ref", "libpocketfft_ref.so")
+    ref, kind, cores = reference_lib()
     rng = np.random.default_rng(1)
-    rows = sample_rows or H
-    x = rng.standard_normal((rows, W), dtype=np.float32)
-    out = np.empty((rows, W // 2 + 1), dtype=np.complex64)
-    if os.path.exists(so):
-        from rocket_fft_b200._abi import LowLevelLib
-
-        ref = LowLevelLib(so)
-        kind = "reference"
-
-        def run():
-            ref.r2c(x, out, [0, 1], True, 1.0, cores)
-    else:
-        from oracle import pocketfft_oracle as O
-
-        kind = "port"
-        cores = 1
-
-        def run():
-            O.r2c(x, out, [0, 1], True, 1.0)
+    x = rng.standard_normal((images, H, W), dtype=np.float32)
+    out = np.empty((images, H, W // 2 + 1), dtype=np.complex64)
     for _ in range(max(1, warmup)):
-        run()
+        ref.r2c(x, out, [1, 2], True, 1.0, cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        run()
+        ref.r2c(x, out, [1, 2], True, 1.0, cores)
     dt = (time.perf_counter() - t0) / steps
-    n = rows * W
-    fl = 2.5 * n * math.log2(n)
-    return {"value": fl / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
-            "sample": f"rfft2 of one float32 {rows}x{W} image via r2c(axes=[0,1]), nthreads={cores}, mean of {steps}",
-            "ms_per_image": dt * 1e3}
+    return {"value": images * flops_per_image() / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
+            "sample": f"rfft2 of {images} float32 {H}x{W} image(s) per step via r2c(axes=[1,2]), nthreads={cores}, "
+                      f"mean of {steps} steps after {max(1, warmup)} warm-up",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference_arm(args, world):
+    # a step is bounded: at most `images` images whatever N is (the host cores do not grow with the GPU count)
+    r = cpu_reference_rfft2(args.images, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(args, world),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def rel_l2(a, b):
+    import numpy as np
+
+    a = np.asarray(a).astype(np.complex128).ravel()
+    b = np.asarray(b).astype(np.complex128).ravel()
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
 def main():
@@ -146,31 +187,21 @@ def main():
     ap.add_argument("--images", type=int, default=4, help="images per GPU per step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fftn", action="store_true")
+    ap.add_argument("--no-other", action="store_true")
+    ap.add_argument("--fftn-n", type=int, default=1024)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    warmup = max(args.warmup, 3)
-
-    config = {"workload": WORKLOAD, "images_per_gpu": args.images, "image": [H, W], "axes": [1, 2],
-              "flops_per_image": flops_per_image(), "algorithmic_bytes_per_image": alg_bytes_per_image(),
-              "l2_policy": "inputs (1 GiB per image) are far larger than the 126 MB L2; no flush needed",
-              "parallelism": f"batch-sharded x{max(world, args.gpus)} (no collective)"}
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        steps = min(args.steps, 5)
-        r = cpu_reference_rfft2(steps, 1)
-        line = {"impl": "reference", "metric": "rfft2 GFLOP/s (2.5*N*log2N per real image)", "value": r["value"],
-                "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_image"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, images_per_gpu=1),
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
+        if rank == 0:
+            run_reference_arm(args, max(world, args.gpus))
         return
+
+    warmup = max(args.warmup, 3)
+    config = make_config(args, world)
 
     import numpy as np
     import torch
@@ -195,6 +226,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
     for _ in range(warmup):
         step()
     barrier()
@@ -210,105 +248,174 @@ def main():
     e1.record()
     barrier()
     launches = R.launch_count()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * B * flops_per_image() / (ms_per_step * 1e-3) / 1e9
 
-    # ---- per-stage timing (rank 0): which kernel dominates, and its roofline --------------------
-    stages = []
-    roofline = None
-    if rank == 0:
-        def timeit(fn, reps):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
+    def timeit(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
 
+    # ---- per-stage timing (rank 0): which kernel dominates, and its roofline ----------------------------
+    stages, roofline, parity = [], None, None
+    if rank == 0:
         reps = max(5, min(args.steps, 20))
-        R.launch_count_reset()
+
+        def traced(fn):
+            R.launch_trace(True)
+            fn()
+            torch.cuda.synchronize()
+            names = R.launch_trace_get()
+            R.launch_trace(False)
+            return names
+
+        row_names = traced(lambda: R.r2c(x, X, [2], True, 1.0))
         t_row = timeit(lambda: R.r2c(x, X, [2], True, 1.0), reps)
-        row_launches = R.launch_count() // (reps + 3)
-        R.launch_count_reset()
+        col_names = traced(lambda: R.c2c(X, X, [1], True, 1.0))
         t_col = timeit(lambda: R.c2c(X, X, [1], True, 1.0), reps)
-        col_launches = R.launch_count() // (reps + 3)
+        step_names = traced(step)
         row_bytes = B * alg_bytes_per_image()
         col_bytes = B * 2 * H * (W // 2 + 1) * 8
         stages = [
-            {"stage": "r2c rows (n=16384 real -> 8193 complex)", "ms": t_row, "launches": row_launches,
+            {"stage": "r2c rows (n=16384 real -> 8193 complex)", "ms": t_row, "launches": len(row_names), "kernels": row_names,
              "algorithmic_GBps": row_bytes / t_row / 1e6},
-            {"stage": "c2c columns (n=16384, stride 65544 B, in place)", "ms": t_col, "launches": col_launches,
-             "algorithmic_GBps": col_bytes / t_col / 1e6},
+            {"stage": "c2c columns (n=16384, stride 65544 B, in place)", "ms": t_col, "launches": len(col_names),
+             "kernels": col_names, "algorithmic_GBps": col_bytes / t_col / 1e6},
         ]
         peak, peak_src = load_peaks()
-        # dominant kernel: the stage with the larger per-launch time
-        dual = int(os.environ.get("RFB200_DUAL", "2"))
-        row_kernel = ("fft_pow2_dual_kernel<12,1,%s> r2c rows" % ("true" if dual == 2 else "false")) if dual else \
-            "fft_pow2_kernel<float,13,1,1> r2c rows"
-        per_launch = [(t_row / max(row_launches, 1), row_bytes, row_kernel, row_launches),
-                      (t_col / max(col_launches, 1), col_bytes,
-                       "fft_fourstep_fused_kernel<float,7,32> columns (both four-step passes, intermediate in L2)" if col_launches == 1
-                       else ("fft_pow2_pair_kernel<7,32> four-step column pass" if int(os.environ.get("RFB200_PAIR", "1"))
-                             else "fft_pow2_kernel<float,7,32,0> four-step column pass"), col_launches)]
+        # the dominant kernel = the stage with the largest time per launch (a stage's launches are the same kernel or,
+        # for the two-launch four-step, two instances of it)
+        per_launch = [(t_row / max(len(row_names), 1), row_bytes, row_names), (t_col / max(len(col_names), 1), col_bytes, col_names)]
         dom = max(per_launch, key=lambda p: p[0])
         achieved = dom[1] / (dom[0] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel for ONE image, from the
-        # committed `ncu --set full` capture (profiles/r01_traffic.json names the report); x images per launch
+        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel for ONE image, from the committed `ncu --set full`
+        # capture (profiles/r02_traffic.json names the report); x images per launch
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                key = "rows" if dom[2].endswith("r2c rows") else ("cols_fused" if "fused" in dom[2] else "cols_pass")
-                traffic = tj[key]["dram_bytes_per_image"] * B
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": dom[2], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[0],
+        for tname in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                try:
+                    tj = json.load(open(tpath))
+                    ent = tj.get("kernels", {}).get(dom[2][0].split("<")[0]) if "kernels" in tj else None
+                    if ent:
+                        traffic = ent["dram_bytes_per_image"] * B
+                        break
+                except Exception:
+                    pass
+        roofline = {"bound": "hbm", "kernel": dom[2][0] if dom[2] else None, "kernels_of_one_step": step_names,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[0],
                     "whole_step_frac_of_compulsory": (B * alg_bytes_per_image() / (ms_per_step * 1e-3) / 1e9) / peak}
+        # ---- parity of the timed path against the reference's CPU result of the same input (image 0) -------
+        try:
+            ref, kind, cores = reference_lib()
+            step()
+            torch.cuda.synchronize()
+            hx = x[0].cpu().numpy()
+            want = np.empty((H, W // 2 + 1), dtype=np.complex64)
+            ref.r2c(hx, want, [0, 1], True, 1.0, cores)
+            err = rel_l2(X[0].cpu().numpy(), want)
+            bound = 1e-5 * math.log2(H * W)
+            parity = {"parity_rel_l2": err, "bound": bound, "ok": bool(err <= bound), "against": f"oracle/_ref ({kind}), image 0 of the step",
+                      "tolerance": "1e-5*log2(n), n = 16384*16384"}
+            del hx, want
+        except Exception as e:  # pragma: no cover
+            parity = {"parity_rel_l2": None, "error": repr(e)}
 
-    # ---- end to end through the C ABI with pinned host buffers (rank-local, max over ranks) -----
+    # ---- end to end through the C ABI with HOST buffers (every rank; max over ranks) ---------------------------
     e2e = None
     if not args.no_e2e:
-        # the same step (B images) through the C ABI from pinned host memory; the library pipelines the
-        # images (H2D of one overlaps kernels / D2H of the previous one)
         hx = torch.empty(B, H, W, dtype=torch.float32, pin_memory=True)
         hx.copy_(x)
         hX = torch.empty(B, H, W // 2 + 1, dtype=torch.complex64, pin_memory=True)
         nx, nX = hx.numpy(), hX.numpy()
-        for _ in range(2):
-            R.r2c(nx, nX, [1, 2], True, 1.0)
-        barrier()
         k = max(3, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(k):
-            R.r2c(nx, nX, [1, 2], True, 1.0)
-        dt = (time.perf_counter() - t0) / k
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * B * flops_per_image() / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": B * H * W * 4,
-               "d2h_bytes_per_step": B * H * (W // 2 + 1) * 8, "ms_per_step": dt * 1e3,
+
+        def wall(fn, reps, warm=2):
+            for _ in range(warm):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return max_over_ranks((time.perf_counter() - t0) / reps)
+
+        dt = wall(lambda: R.r2c(nx, nX, [1, 2], True, 1.0), k)
+        h2d_b, d2h_b = B * H * W * 4, B * H * (W // 2 + 1) * 8
+        e2e = {"value": world * B * flops_per_image() / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d_b,
+               "d2h_bytes_per_step": d2h_b, "ms_per_step": dt * 1e3,
                "call": f"numba_r2c via rocket_fft_b200.r2c(numpy pinned in/out), {B} images per step per rank, "
                        "image-pipelined H2D / kernels / D2H inside the call"}
-        # cheap parity spot check of the e2e result against the device-resident result
+        # parity of the e2e result against the device-resident result (itself checked against the reference above)
         step()
         torch.cuda.synchronize()
-        chk = float(torch.linalg.vector_norm(torch.view_as_real(hX[:, :4].to(dev) - X[:, :4])) /
-                    torch.linalg.vector_norm(torch.view_as_real(X[:, :4])))
-        e2e["matches_device_path_rel_l2"] = chk
+        e2e["matches_device_path_rel_l2"] = float(torch.linalg.vector_norm(torch.view_as_real(hX[:, :4].to(dev) - X[:, :4])) /
+                                                  torch.linalg.vector_norm(torch.view_as_real(X[:, :4])))
+        # the copies alone: what the link allows (no kernels)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def h2d_only():
+            x.copy_(hx, non_blocking=True)
+            torch.cuda.synchronize()
+
+        def d2h_only():
+            hX.copy_(X, non_blocking=True)
+            torch.cuda.synchronize()
+
+        def both():
+            with torch.cuda.stream(s1):
+                x.copy_(hx, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hX.copy_(X, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e["h2d_ms"] = wall(h2d_only, 3, 1) * 1e3
+        e2e["d2h_ms"] = wall(d2h_only, 3, 1) * 1e3
+        e2e["copy_only_ms"] = wall(both, 3, 1) * 1e3
+        e2e["h2d_GBps"] = h2d_b / e2e["h2d_ms"] / 1e6
+        e2e["d2h_GBps"] = d2h_b / e2e["d2h_ms"] / 1e6
+        e2e["frac_of_copy_only"] = e2e["copy_only_ms"] / e2e["ms_per_step"]
+        del hx, hX, nx, nX
+        # the drop-in case: plain (pageable) NumPy arrays, as an @njit caller has them
+        try:
+            px = np.empty((B, H, W), dtype=np.float32)
+            px[...] = 0.5
+            pX = np.empty((B, H, W // 2 + 1), dtype=np.complex64)
+            dtp = wall(lambda: R.r2c(px, pX, [1, 2], True, 1.0), 3, 2)
+            e2e["e2e_pageable"] = {"value": world * B * flops_per_image() / dtp / 1e9, "unit": "GFLOP/s", "ms_per_step": dtp * 1e3,
+                                   "frac_of_pinned": dt / dtp,
+                                   "call": "the same call on plain NumPy arrays (pageable host memory)"}
+            del px, pX
+        except Exception as e:  # pragma: no cover
+            e2e["e2e_pageable"] = {"error": repr(e)}
+
+    del x, X
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2]: fftn complex64 1024^3 on the same N GPUs ---------------------------------------------
+    fftn = None
+    if not args.no_fftn:
+        try:
+            fftn = bench_fftn(args, R, torch, dist, dev, rank, world, barrier, max_over_ranks)
+        except Exception as e:  # pragma: no cover
+            fftn = {"error": repr(e)}
+        torch.cuda.empty_cache()
+
+    other = None
+    if rank == 0 and world == 1 and not args.no_other:
+        try:
+            other = bench_other_configs(R, torch, dev, timeit)
+        except Exception as e:  # pragma: no cover
+            other = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -317,19 +424,154 @@ def main():
 
     cpu = None
     if not args.no_cpu and world == 1:
-        r = cpu_reference_rfft2(3, 1)
+        r = cpu_reference_rfft2(1, 10, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    line = {"metric": "rfft2 GFLOP/s (2.5*N*log2N per real image)", "value": value, "unit": "GFLOP/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+    line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "parity": parity,
+            "parity_rel_l2": parity.get("parity_rel_l2") if parity else None,
             # the BASELINE label's "5N*log2N" applied verbatim to real data is exactly twice `value`
-            "value_5NlogN_label": 2.0 * value,
-            "clocks": clocks, "stages": stages, "library": R.version()}
+            "value_5NlogN_label": 2.0 * value, "clocks": clocks, "stages": stages, "fftn": fftn, "other_configs": other,
+            "library": R.version()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_fftn(args, R, torch, dist, dev, rank, world, barrier, max_over_ranks):
+    """fftn of a complex64 n^3 volume: N = 1 one c2c(axes=[0,1,2]) call; N > 1 slab decomposition (SlabFFTN, default
+    engine).  Parity: the same code path at 512^3 against the reference on the host (rank 0 gathers the shards)."""
+    import numpy as np
+
+    from rocket_fft_b200.distributed import SlabFFTN, shard_batch
+
+    n = args.fftn_n
+    steps = max(3, min(args.steps, 10))
+    flops = 5.0 * n**3 * math.log2(n**3)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, k):
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / k)
+
+    res = {"workload": f"cfg3: fftn complex64 {n}^3, axes=[0,1,2]", "n_gpus": world, "scaling": "strong"}
+    # ---- parity at 512^3 through the same path ---------------------------------------------------------------------------
+    pn = min(512, n)
+    rng = np.random.default_rng(2)
+    if rank == 0:
+        full = (rng.standard_normal((pn, pn, pn), dtype=np.float32) + 1j * rng.standard_normal((pn, pn, pn), dtype=np.float32)).astype(np.complex64)
+    else:
+        full = None
+    if world == 1:
+        v = torch.from_numpy(full).to(dev)
+        V = torch.empty_like(v)
+        R.c2c(v, V, [0, 1, 2], True, 1.0)
+        got = V.cpu().numpy()
+        del v, V
+    else:
+        ft = torch.from_numpy(full).to(dev) if rank == 0 else torch.empty(pn, pn, pn, dtype=torch.complex64, device=dev)
+        dist.broadcast(ft, 0)
+        lo, hi = shard_batch(pn, rank, world)
+        plan = SlabFFTN((pn, pn, pn), torch.complex64, dev)
+        y = plan.forward(ft[lo:hi].clone(), True, 1.0).contiguous()  # (pn, pn/P, pn): axis 1 sharded
+        parts = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
+        dist.gather(y, parts, dst=0)
+        got = torch.cat(parts, dim=1).cpu().numpy() if rank == 0 else None
+        res["exchange_engine"] = plan.mode
+        del ft, y, parts, plan
+    if rank == 0:
+        ref, kind, cores = reference_lib()
+        want = np.empty_like(full)
+        ref.c2c(full, want, [0, 1, 2], True, 1.0, cores)
+        err = rel_l2(got, want)
+        bound = 1e-5 * math.log2(pn**3)
+        res.update({"parity_rel_l2": err, "parity_bound": bound, "parity_ok": bool(err <= bound),
+                    "parity_case": f"{pn}^3 through the same path vs oracle/_ref ({kind})"})
+        del want, got
+    del full
+    torch.cuda.empty_cache()
+    # ---- timing at n^3 --------------------------------------------------------------------------------------------------
+    if world == 1:
+        x = torch.randn(n, n, n, dtype=torch.complex64, device=dev)
+        y = torch.empty_like(x)
+        for _ in range(3):
+            R.c2c(x, y, [0, 1, 2], True, 1.0)
+        ms = timed(lambda: R.c2c(x, y, [0, 1, 2], True, 1.0), steps)
+        axes_ms = {f"axis{ax}": timed(lambda: R.c2c(x, y, [ax], True, 1.0), steps) for ax in (0, 1, 2)}
+        res.update({"ms": ms, "alltoall_ms": None, "bus_GBps": None, "frac_of_900": None, "GFLOPs": flops / ms / 1e6,
+                    "compulsory_GBps": 2 * 8 * n**3 / ms / 1e6, "stages_ms": axes_ms,
+                    "layout": "single device: natural order in and out",
+                    "limiter": "axis " + max(axes_ms, key=axes_ms.get)[-1] + " pass (strided lines)"})
+        return res
+    plan = SlabFFTN((n, n, n), torch.complex64, dev)
+    g = torch.Generator(device=dev).manual_seed(2 + rank)
+    x = torch.randn(n // world, n, n, dtype=torch.complex64, device=dev, generator=g)
+    for _ in range(3):
+        plan.forward(x, True, 1.0)
+    total_ms = timed(lambda: plan.forward(x, True, 1.0), steps)
+    if plan.mode == "fused":
+        a2a_ms = timed(lambda: plan.scatter_axis1(x, True), steps)  # axis-1 transform + NVLink push: one kernel
+        planes_ms = timed(lambda: R.c2c(x, x, [2], True, 1.0), steps)
+    else:
+        a2a_ms = timed(lambda: plan.exchange(x), steps)
+        planes_ms = timed(lambda: plan.local_planes(x, True, 1.0), steps)
+    axis0_ms = timed(lambda: plan.local_axis0(True), steps)
+    bus = plan.bytes_sent_per_rank / a2a_ms / 1e6
+    st = {"local_planes": planes_ms, "alltoall": a2a_ms, "axis0": axis0_ms}
+    res.update({"ms": total_ms, "alltoall_ms": a2a_ms, "bus_GBps": bus, "frac_of_900": bus / 900.0, "frac_of_measured_770": bus / 770.0,
+                "GFLOPs": flops / total_ms / 1e6, "bytes_sent_per_gpu": plan.bytes_sent_per_rank, "stages_ms": st,
+                "exchange": plan.mode + {"symm": " (pack fused into the push)", "nccl": " (pack + all_to_all_single)",
+                                         "fused": " (the axis-1 FFT kernel stores straight into peer HBM over NVLink; alltoall_ms = that kernel incl. its butterflies)"}[plan.mode],
+                "layout": "result left axis-1 sharded (transposed); transpose_back available",
+                "limiter": max(st, key=st.get)})
+    return res
+
+
+def bench_other_configs(R, torch, dev, timeit):
+    """The remaining BASELINE configs, device-resident, algorithmic (compulsory) bytes / time (CUDA events)."""
+    peak, _ = load_peaks()
+    out = []
+
+    def row(name, fn, nbytes, reps=10):
+        R.launch_count_reset()
+        ms = timeit(fn, reps)
+        out.append({"config": name, "ms": ms, "algorithmic_GBps": nbytes / ms / 1e6, "frac_of_peak": nbytes / ms / 1e6 / peak,
+                    "launches_per_call": R.launch_count() // (reps + 3)})
+
+    x = torch.randn(4096, 4096, dtype=torch.complex128, device=dev)
+    y = torch.empty_like(x)
+    row("cfg1 c2c complex128 (4096,4096) axes=[1]", lambda: R.c2c(x, y, [1], True, 1.0), 2 * x.numel() * 16, 20)
+    del x, y
+    x = torch.randn(256, 15015, dtype=torch.complex64, device=dev)
+    y = torch.empty_like(x)
+    row("cfg4a c2c complex64 (256,15015) axes=[1]", lambda: R.c2c(x, y, [1], True, 1.0), 2 * x.numel() * 8, 20)
+    del x, y
+    x = torch.randn(256, 1000003, dtype=torch.complex64, device=dev)
+    y = torch.empty_like(x)
+    row("cfg4b c2c complex64 (256,1000003) axes=[1] (Bluestein)", lambda: R.c2c(x, y, [1], True, 1.0), 2 * x.numel() * 8, 3)
+    del x, y
+    x = torch.randn(2048, 2048, 64, dtype=torch.float64, device=dev)
+    y = torch.empty_like(x)
+    row("cfg5 dct type 2 float64 (2048,2048,64) axes=[0,1]", lambda: R.dct(x, y, [0, 1], 2, 1.0, False), 2 * x.numel() * 8, 3)
+    row("cfg5 dst type 2 float64 (2048,2048,64) axes=[0,1]", lambda: R.dst(x, y, [0, 1], 2, 1.0, False), 2 * x.numel() * 8, 3)
+    del x, y
+    x = torch.randn(4, 16384, 8193, dtype=torch.complex64, device=dev)
+    y = torch.empty(4, 16384, 16384, dtype=torch.float32, device=dev)
+    row("cfg2 inverse: irfft2 (c2r axes=[1,2]) of 4 half spectra 16384x8193", lambda: R.c2r(x, y, [1, 2], False, 1.0),
+        x.numel() * 8 + y.numel() * 4, 5)
+    del x, y
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

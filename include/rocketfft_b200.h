@@ -167,6 +167,11 @@ void rfb200_use_library_stream(void);
 /* Number of kernel launches issued by this library since the last reset (all threads). */
 uint64_t rfb200_launch_count(void);
 void rfb200_launch_count_reset(void);
+/* Launch trace: rfb200_launch_trace(1) starts (and clears) a record of the names of the kernels launched, (0) stops it;
+ * rfb200_launch_trace_get returns them as one ';'-separated string (valid until the calling thread's next call).
+ * Lets a benchmark name the kernels it timed from what actually ran. */
+void rfb200_launch_trace(int enable);
+const char *rfb200_launch_trace_get(void);
 /* DST-II/III with ortho=true: 1 (default) reproduces the reference, which scales element
  * 0 (H:3033-3039, README.md:61-65); 0 scales element N-1 as SciPy does. */
 void rfb200_set_dst_ortho_quirk(int enabled);

@@ -17,6 +17,8 @@ from .lowlevel import (  # noqa: F401
     last_error,
     launch_count,
     launch_count_reset,
+    launch_trace,
+    launch_trace_get,
     lib,
     plan_cache_clear,
     r2c,

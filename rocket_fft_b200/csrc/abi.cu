@@ -435,6 +435,12 @@ RFB_EXPORT void rfb200_set_stream(void *stream) {
 }
 RFB_EXPORT void rfb200_use_library_stream(void) { g_user_stream_set = false; }
 RFB_EXPORT uint64_t rfb200_launch_count(void) { return rfb::launch_count(); }
+RFB_EXPORT void rfb200_launch_trace(int enable) { rfb::launch_trace_enable(enable != 0); }
+RFB_EXPORT const char *rfb200_launch_trace_get(void) {
+    static thread_local std::string buf;
+    buf = rfb::launch_trace_get();
+    return buf.c_str();
+}
 RFB_EXPORT void rfb200_launch_count_reset(void) { rfb::launch_count_reset(); }
 RFB_EXPORT void rfb200_set_dst_ortho_quirk(int enabled) { rfb::set_dst_ortho_quirk(enabled != 0); }
 RFB_EXPORT int64_t rfb200_debug_fuse4_unit(uint32_t unit, uint32_t nstrips, uint32_t lag) {

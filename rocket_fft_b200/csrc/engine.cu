@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <string>
 #include <stdlib.h>
 #include <string.h>
 
@@ -22,13 +23,36 @@ namespace rfb {
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 void launch_count_reset() { g_launches.store(0); }
-void count_launch() { g_launches.fetch_add(1); }
+// Launch trace (rfb200_launch_trace): the names of the kernels launched since the last reset, so that a benchmark can name
+// the kernel it times from what actually ran.
+static std::mutex g_trace_mu;
+static std::vector<std::string> g_trace;
+static std::atomic<bool> g_trace_on{false};
+void launch_trace_enable(bool on) {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_trace_on.store(on);
+    g_trace.clear();
+}
+std::string launch_trace_get() {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    std::string r;
+    for (auto &n : g_trace) { if (!r.empty()) r += ";"; r += n; }
+    return r;
+}
+void count_launch(const char *name) {
+    g_launches.fetch_add(1);
+    if (g_trace_on.load() && name) {
+        std::lock_guard<std::mutex> lk(g_trace_mu);
+        if (g_trace.size() < 256) g_trace.push_back(name);
+    }
+}
 
-#define RFB_AFTER_LAUNCH()                      \
+#define RFB_AFTER_LAUNCH_N(name)                 \
     do {                                        \
-        g_launches.fetch_add(1);                \
+        count_launch(name);                     \
         RFB_CUDA_CHECK(cudaGetLastError());     \
     } while (0)
+#define RFB_AFTER_LAUNCH() RFB_AFTER_LAUNCH_N("engine helper kernel")
 
 static const size_t MAX_SMEM = 227 * 1024;
 
@@ -304,7 +328,7 @@ static void launch_tile_typed(const LineJob &job, const std::vector<Dim> &dims, 
         dev_set = dev;
     }
     kern<<<(unsigned)ntiles, tp.threads, tp.smem, s>>>(g);
-    RFB_AFTER_LAUNCH();
+    RFB_AFTER_LAUNCH_N(sizeof(T) == 8 ? "fft_tile_kernel<double>" : "fft_tile_kernel<float>");
 }
 
 static void launch_tile(const LineJob &job, const std::vector<Dim> &dims, const TilePlan &tp, cudaStream_t s) {
@@ -529,8 +553,8 @@ static bool fourstep_fused(const LineJob &job, const std::vector<Dim> &dims, uin
     // the 128-point line-fast tiles are limited by instruction issue and load latency on the SM, not by DRAM, so halving
     // the DRAM traffic buys nothing until the tile body itself is leaner.  (Read per call so that tests can switch it.)
     const char *on_env = getenv("RFB200_FUSE4");
-    const int on = on_env ? atoi(on_env) : 0;
-    if (!on || job.prec != 0 || n1 != n2 || n1 != 128) return false;
+    const int on = on_env ? atoi(on_env) : 2;
+    if (on != 1 || job.prec != 0 || n1 != n2 || n1 != 128) return false;
     if (job.load_mode != LD_C2C || job.store_mode != ST_C2C || job.flags || (job.n_in && job.n_in != job.n) || job.twN ||
         job.pre_tab || job.post_tab || !job.split_out.empty() || job.conv)
         return false;
@@ -603,6 +627,10 @@ static bool fourstep_fused(const LineJob &job, const std::vector<Dim> &dims, uin
 static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
     uint64_t n1, n2;
     choose_split(job.n, job.prec, n1, n2);
+    // RFB200_FUSE4: 0 = two launches, 1 = the ticket-per-CTA fused kernel of round 1, 2 (default) = the warp-specialised
+    // fused kernel fed by the copy engine (fused4v2_kernel.cuh).  Read per call so that tests can switch it.
+    const char *f4 = getenv("RFB200_FUSE4");
+    if ((!f4 || atoi(f4) >= 2) && launch_fourstep_fused2_f32(job, dims, s)) return;
     if (fourstep_fused(job, dims, n1, n2, s)) return;
     run_fourstep_plain(job, dims, s);
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
 #include <vector>
 
 #include "modes.h"
@@ -83,7 +84,11 @@ void op_genuine_hartley(const NdArgs &a, cudaStream_t s);
 // data[l][j] *= table[j] over `nlines` contiguous lines of n items (real or complex, same precision as the table)
 void op_scale_lines(int prec, bool cplx, uint64_t nlines, uint64_t n, const void *table, void *data, cudaStream_t s);
 
+// sticky report of a kernel-side failure (fused4v2_launch.cu): throws Error if a kernel flagged one since the last check
+void check_async_error();
 uint64_t launch_count();
+void launch_trace_enable(bool on);
+std::string launch_trace_get();
 void launch_count_reset();
 void set_dst_ortho_quirk(bool on);
 

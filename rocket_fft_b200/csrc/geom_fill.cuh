@@ -12,7 +12,7 @@
 
 namespace rfb {
 
-void count_launch();
+void count_launch(const char *name = nullptr);
 
 template <typename T>
 inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<Dim> &dims, uint32_t W, bool load_lf,
@@ -150,6 +150,8 @@ bool launch_pow2_f64(const LineJob &job, const std::vector<Dim> &dims, bool load
 // pow2_launch_f32.cu: fused four-step (both steps in one persistent kernel, intermediate in L2); false if not taken
 bool launch_fourstep_fused_f32(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB,
                                const Fuse4Ctl &c, cudaStream_t s);
+// fused4v2_launch.cu: both four-step passes of 16384-point strided complex64 lines in one warp-specialised persistent kernel
+bool launch_fourstep_fused2_f32(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 // jit.cu: run-time specialised kernel for smooth non-power-of-two lengths (NVRTC); false if not taken
 bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
                      cudaStream_t s);

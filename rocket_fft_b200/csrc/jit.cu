@@ -384,7 +384,11 @@ bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load
     };
     if (job.prec) launch(double());
     else launch(float());
-    count_launch();
+    {
+        char nm[64];
+        snprintf(nm, sizeof nm, "fft_spec_kernel<%s,n=%llu> (NVRTC)", job.prec ? "double" : "float", (unsigned long long)job.n);
+        count_launch(nm);
+    }
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;
 }

@@ -15,7 +15,7 @@ static bool g_dst_quirk = true;
 void set_dst_ortho_quirk(bool on) { g_dst_quirk = on; }
 
 #define RFB_AFTER_LAUNCH2() RFB_CUDA_CHECK(cudaGetLastError())
-extern void count_launch();
+void count_launch(const char *name = nullptr);
 
 static bool any_zero(const std::vector<int64_t> &s) {
     for (auto v : s)

@@ -1,6 +1,7 @@
 // Dispatch of a line job onto the instantiations of fft_pow2_kernel (one translation unit per
 // precision, see pow2_launch_f32.cu / pow2_launch_f64.cu).
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "geom_fill.cuh"
@@ -63,7 +64,11 @@ bool launch_dual_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
         dev_set = dev;
     }
     kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
-    count_launch();
+    {
+        char nm[64];
+        snprintf(nm, sizeof nm, "fft_pow2_dual_kernel<%d,%d,%s>", LOGNH, MODE, TWC ? "true" : "false");
+        count_launch(nm);
+    }
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;
 }
@@ -134,7 +139,11 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
         dev_set = dev;
     }
     kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
-    count_launch();
+    {
+        char nm[64];
+        snprintf(nm, sizeof nm, "fft_pow2_kernel<%s,%d,%d,%d>", sizeof(T) == 8 ? "double" : "float", LOGN, W, MODE);
+        count_launch(nm);
+    }
     RFB_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -252,7 +261,11 @@ bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
         dev_set = dev;
     }
     kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
-    count_launch();
+    {
+        char nm[64];
+        snprintf(nm, sizeof nm, "fft_pow2_pair_kernel<%d,%d>", LOGN, W);
+        count_launch(nm);
+    }
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;
 }
@@ -279,7 +292,7 @@ bool launch_async_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStr
     static const int per_sm = [] { const char *v = getenv("RFB200_ASYNC_CTAS"); return v ? atoi(v) : 3; }();
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1));
     kern<<<grid, Body::NT, smem, s>>>(g, stw, (uint32_t)ntiles);
-    count_launch();
+    count_launch("fft_pow2_async_kernel");
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;
 }
@@ -318,7 +331,7 @@ bool launch_fused4_logn(const LineJob &A, const std::vector<Dim> &dA, const Line
     const uint64_t items = 2ull * c.nstrips * c.tiles;
     const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)sms * (uint64_t)per_sm);
     kern<<<grid, Body::NT, smem, s>>>(gA, gB, stw, c);
-    count_launch();
+    count_launch("fft_fourstep_fused_kernel<float,7,32>");
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;
 }

@@ -82,3 +82,89 @@ extern "C" __attribute__((visibility("default"))) int rfb200_debug_tile_copy(con
                                                                    tiles0, mode);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
+
+// ---- round 2 probes: bandwidth of an L2-resident working set, and of distributed shared memory inside a cluster -----------
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+namespace {
+
+// mode 0: read only (16-byte loads, summed), 1: copy in -> out.  Every CTA sweeps the whole buffer `reps` times, starting
+// at a CTA-dependent offset so that the CTAs do not walk in lockstep.
+__global__ void __launch_bounds__(512, 2) l2_sweep_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, uint64_t n16, int reps,
+                                                        int mode, float *sink) {
+    float acc = 0.f;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < reps; ++r) {
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n16; i += 4 * stride) {
+            float4 a = __ldcg(in + i), b = __ldcg(in + i + stride), c = __ldcg(in + i + 2 * stride), d = __ldcg(in + i + 3 * stride);
+            if (mode) { __stcg(out + i, a); __stcg(out + i + stride, b); __stcg(out + i + 2 * stride, c); __stcg(out + i + 3 * stride, d); }
+            else acc += a.x + b.y + c.z + d.w;
+        }
+        for (; i < n16; i += stride) {
+            float4 a = __ldcg(in + i);
+            if (mode) __stcg(out + i, a);
+            else acc += a.x;
+        }
+    }
+    if (acc == 12345.678f) *sink = acc;
+}
+
+// Every CTA of a cluster writes (mode 0) / reads (mode 1) `kb` KiB to / from EACH other CTA's shared memory, `reps` times.
+// cycles[cta] = SM cycles the exchange took.
+__global__ void __launch_bounds__(256, 1) dsmem_kernel(uint32_t kb, int reps, int mode, unsigned long long *cycles, float *sink) {
+    extern __shared__ __align__(16) unsigned char smem_probe[];
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned nr = cl.num_blocks(), me = cl.block_rank();
+    float4 *mine = reinterpret_cast<float4 *>(smem_probe);
+    const uint32_t n16 = kb * 64u;  // 16-byte items per peer region
+    for (uint32_t i = threadIdx.x; i < n16 * nr; i += blockDim.x) mine[i] = make_float4((float)i, 1.f, 2.f, 3.f);
+    cl.sync();
+    float acc = 0.f;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+        for (unsigned d = 1; d < nr; ++d) {
+            const unsigned peer = (me + d) % nr;
+            float4 *remote = cl.map_shared_rank(mine, peer) + (size_t)me * n16;  // my slot in the peer's buffer
+            if (mode == 0) {
+                for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) remote[i] = make_float4(acc, (float)i, 0.f, 1.f);
+            } else {
+                for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) { const float4 v = remote[i]; acc += v.x + v.w; }
+            }
+        }
+    }
+    cl.sync();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+    if (acc == 12345.678f) *sink = acc;
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int rfb200_debug_l2_sweep(const void *in, void *out, uint64_t bytes, int reps, int mode,
+                                                                            uint32_t ctas, void *sink, void *stream) {
+    l2_sweep_kernel<<<ctas, 512, 0, (cudaStream_t)stream>>>((const float4 *)in, (float4 *)out, bytes / 16, reps, mode, (float *)sink);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+extern "C" __attribute__((visibility("default"))) int rfb200_debug_dsmem(uint32_t cluster, uint32_t nclusters, uint32_t kb, int reps, int mode,
+                                                                         void *cycles, void *sink, void *stream) {
+    const size_t smem = (size_t)kb * 1024 * cluster;
+    if (cluster < 2 || cluster > 16 || smem > 227 * 1024) return 1;
+    if (cudaFuncSetAttribute(dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+    if (cluster > 8 && cudaFuncSetAttribute(dsmem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster * nclusters);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, dsmem_kernel, kb, reps, mode, (unsigned long long *)cycles, (float *)sink);
+    return e == cudaSuccess ? 0 : 2;
+}

@@ -25,7 +25,7 @@ static void launch_regmix_inst(const LineJob &job, const std::vector<Dim> &dims,
         dev_set = dev;
     }
     kern<<<(unsigned)ntiles, W * pl.TPL, smem, s>>>(g, pl);
-    count_launch();
+    count_launch(sizeof(T) == 8 ? "fft_regmix_kernel<double>" : "fft_regmix_kernel<float>");
     RFB_CUDA_CHECK(cudaGetLastError());
 }
 

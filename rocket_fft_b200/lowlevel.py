@@ -86,6 +86,21 @@ def launch_count_reset() -> None:
     _c.rfb200_launch_count_reset()
 
 
+_c.rfb200_launch_trace.argtypes = [C.c_int]
+_c.rfb200_launch_trace_get.restype = C.c_char_p
+
+
+def launch_trace(enable: bool) -> None:
+    """Start (and clear) / stop the record of kernel names launched by the library."""
+    _c.rfb200_launch_trace(1 if enable else 0)
+
+
+def launch_trace_get():
+    """Names of the kernels launched since launch_trace(True), in launch order."""
+    s = (_c.rfb200_launch_trace_get() or b"").decode()
+    return s.split(";") if s else []
+
+
 def plan_cache_clear() -> None:
     _c.rfb200_plan_cache_clear()
 

@@ -17,9 +17,9 @@ def reflib():
     """The compiled, unmodified reference (oracle/_ref), or None when it is absent."""
     global _ref
     if _ref is None and os.path.exists(REF_SO):
-        from rocket_fft_b200._abi import LowLevelLib
+        from oracle.abi_view import RefLib  # neutral module: never maps the product's .so
 
-        _ref = LowLevelLib(REF_SO)
+        _ref = RefLib(REF_SO)
     return _ref
 
 

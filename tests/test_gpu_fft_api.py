@@ -98,8 +98,8 @@ def test_torch_device_tensors(F):
     x = torch.randn(16, 1000, dtype=torch.float32, device="cuda")
     X = F.rfft2(x)
     assert X.is_cuda and X.dtype == torch.complex64
-    ref = torch.fft.rfft2(x)
-    assert float(torch.linalg.vector_norm(torch.view_as_real(X - ref)) / torch.linalg.vector_norm(torch.view_as_real(ref))) < 2e-4
+    ref = scipy.fft.rfft2(x.cpu().numpy())
+    assert parity.l2err(X.cpu().numpy(), ref) < 2e-4
     y = F.irfft2(X, s=(16, 1000))
     assert float(torch.linalg.vector_norm(y - x) / torch.linalg.vector_norm(x)) < 2e-4
     d = F.dctn(x.double(), axes=(1,))

@@ -346,19 +346,17 @@ def test_device_arrays_and_full_size_properties(R):
     R.c2r(X, xr, [0, 1], False, 1.0 / x.numel())
     err = float(torch.linalg.vector_norm((xr - x).double()) / torch.linalg.vector_norm(x.double()))
     assert err < parity.tol(np.float32, 2**28), err
-    # spot rows against torch.fft (cuFFT) as a side check
-    ref = torch.fft.rfft2(x[:, :])[:8]
-    err = float(torch.linalg.vector_norm((X[:8] - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
-    assert err < parity.tol(np.float32, 2**28), err
-    del x, X, xr, ref
-    # config 3 at 256^3 (+ linearity), full 1024^3 round trip if memory allows
-    v = torch.randn(256, 256, 256, dtype=torch.complex64, device=dev, generator=g)
+    del x, X, xr
+    # config 3 at 256^3 against the reference, then the full 1024^3 round trip
+    T = trusted()
+    vh = cplx(np.random.default_rng(2), (256, 256, 256), np.complex64)
+    v = torch.from_numpy(vh).to(dev)
     V = torch.empty_like(v)
     R.c2c(v, V, [0, 1, 2], True, 1.0)
-    ref = torch.fft.fftn(v)
-    err = float(torch.linalg.vector_norm((V - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
-    assert err < parity.tol(np.float32, 2**24), err
-    del v, V, ref
+    want = np.empty_like(vh)
+    T.c2c(vh, want, [0, 1, 2], True, 1.0)
+    check(V.cpu().numpy(), want, np.float32, 2**24, "fftn 256^3")
+    del v, V, want, vh
     v = torch.randn(1024, 1024, 1024, dtype=torch.complex64, device=dev, generator=g)
     V = torch.empty_like(v)
     R.c2c(v, V, [0, 1, 2], True, 1.0)
@@ -373,6 +371,101 @@ def test_device_arrays_and_full_size_properties(R):
     R.dct(y, y, [0, 1], 3, 1.0 / (4096.0 * 4096.0), False)
     err = float(torch.linalg.vector_norm(y - x) / torch.linalg.vector_norm(x))
     assert err < parity.tol(np.float64, 4096 * 4096), err
+
+
+def test_baseline_configs_full_size_against_the_reference(R):
+    """The BASELINE configs at FULL size, device result against the compiled reference (oracle/_ref, all host
+    threads) on the same seeded input, under the north-star tolerance: cfg2 r2c AND c2r 16384^2, cfg5 dct AND dst
+    (2048,2048,64), cfg4b Bluestein at 256 rows, and a 512^3 complex64 fftn (cfg3's code path; 1024^3 is 16 GiB of
+    host memory per side and minutes of CPU time)."""
+    import torch
+
+    T = parity.reflib()
+    if T is None:
+        pytest.skip("oracle/_ref did not travel")
+    nt = os.cpu_count() or 1
+    dev = torch.device("cuda:0")
+
+    def gpu(fn, ain, out_shape, out_dtype):
+        d_in = torch.from_numpy(ain).to(dev)
+        d_out = torch.empty(out_shape, dtype=out_dtype, device=dev)
+        fn(d_in, d_out)
+        torch.cuda.synchronize()
+        res = d_out.cpu().numpy()
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        return res
+
+    # ---- cfg2: rfft2 / irfft2 of a float32 16384 x 16384 image --------------------------------------------------------
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((16384, 16384), dtype=np.float32)
+    want = np.empty((16384, 8193), dtype=np.complex64)
+    T.r2c(x, want, [0, 1], True, 1.0, nt)
+    got = gpu(lambda a, b: R.r2c(a, b, [0, 1], True, 1.0), x, (16384, 8193), torch.complex64)
+    check(got, want, np.float32, 2**28, "cfg2 r2c full size")
+    del got
+    wantr = np.empty_like(x)
+    T.c2r(want, wantr, [0, 1], False, 1.0 / 2**28, nt)
+    gotr = gpu(lambda a, b: R.c2r(a, b, [0, 1], False, 1.0 / 2**28), want, (16384, 16384), torch.float32)
+    check(gotr, wantr, np.float32, 2**28, "cfg2 c2r full size")
+    check(gotr, x, np.float32, 2**28, "cfg2 round trip")
+    del x, want, wantr, gotr
+    # ---- cfg5: dctn / dstn type II, float64 (2048, 2048, 64), axes (0, 1) ------------------------------------------------
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2048, 2048, 64))
+    for kind in ("dct", "dst"):
+        want = np.empty_like(x)
+        getattr(T, kind)(x, want, [0, 1], 2, 1.0, False, nt)
+        got = gpu(lambda a, b: getattr(R, kind)(a, b, [0, 1], 2, 1.0, False), x, x.shape, torch.float64)
+        check(got, want, np.float64, 4096 * 4096, "cfg5 full size " + kind)
+        del want, got
+    del x
+    # ---- cfg4b: prime length 1000003 (Bluestein), 256 rows ---------------------------------------------------------------
+    rng = np.random.default_rng(4)
+    x = cplx(rng, (256, 1000003), np.complex64)
+    want = np.empty_like(x)
+    T.c2c(x, want, [1], True, 1.0, nt)
+    got = gpu(lambda a, b: R.c2c(a, b, [1], True, 1.0), x, x.shape, torch.complex64)
+    check(got, want, np.float32, 1000003, "cfg4b full size")
+    del x, want, got
+    # ---- cfg3's path: fftn of a complex64 512^3 volume -----------------------------------------------------------------
+    rng = np.random.default_rng(2)
+    x = cplx(rng, (512, 512, 512), np.complex64)
+    want = np.empty_like(x)
+    T.c2c(x, want, [0, 1, 2], True, 1.0, nt)
+    got = gpu(lambda a, b: R.c2c(a, b, [0, 1, 2], True, 1.0), x, x.shape, torch.complex64)
+    check(got, want, np.float32, 2**27, "fftn 512^3")
+    back = gpu(lambda a, b: R.c2c(a, b, [2, 0, 1], False, 1.0 / 2**27), want, x.shape, torch.complex64)
+    check(back, x, np.float32, 2**27, "ifftn 512^3 (axes permuted)")
+
+
+def test_slab_pipeline_emulated_on_one_device(R):
+    """The kernels of the slab-decomposed fftn (rocket_fft_b200.distributed.SlabFFTN, engine "fused") on ONE device,
+    against the reference: the P ranks are played one after the other, each rank's axis-1 transform scatters its
+    output blocks into the P receive buffers with rfb200_c2c_scatter -- the fused FFT + all-to-all push kernel; on a
+    multi-GPU box those buffers are the peers' NVLink-mapped memory, here they are local -- and the axis-0 transforms
+    follow.  (The real multi-rank run is tests/_slab_check.py under torchrun and bench.py --gpus N.)"""
+    import torch
+
+    T = trusted()
+    dev = torch.device("cuda:0")
+    for shape, ranks in (((128, 128, 128), (2, 8)), ((64, 1024, 96), (2, 4, 8)), ((16, 16384, 8), (4,))):
+        n0, n1, n2 = shape
+        fullh = cplx(np.random.default_rng(21), shape, np.complex64)
+        want = np.empty_like(fullh)
+        T.c2c(fullh, want, [0, 1, 2], True, 1.0)
+        full = torch.from_numpy(fullh).to(dev)
+        for P in ranks:
+            recv = [torch.zeros(P, n0 // P, n1 // P, n2, dtype=torch.complex64, device=dev) for _ in range(P)]
+            for g in range(P):
+                x = full[g * (n0 // P):(g + 1) * (n0 // P)].clone()
+                R.c2c(x, x, [2], True, 1.0)
+                R.c2c_scatter(x, [recv[h][g] for h in range(P)], 1, True, 1.0)
+            for h in range(P):
+                y = recv[h].view(n0, n1 // P, n2)
+                R.c2c(y, y, [0], True, 1.0)
+                torch.cuda.synchronize()
+                check(y.cpu().numpy(), want[:, h * (n1 // P):(h + 1) * (n1 // P)], np.float32, n0 * n1 * n2, ("slab emulation", shape, P, h))
 
 
 def test_numba_njit_calls_run_on_the_gpu(R):
@@ -541,9 +634,9 @@ def test_long_real_lines_two_transforms_per_thread(R):
     xb = torch.from_numpy(rng.standard_normal((1200, n)).astype(np.float32)).to(dev)
     Xb = torch.empty(1200, nb, dtype=torch.complex64, device=dev)
     R.r2c(xb, Xb, [1], True, 1.0)
-    ref = torch.fft.rfft(xb, dim=1)
-    err = float(torch.linalg.vector_norm((Xb - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
-    assert err < parity.tol(np.float32, n), err
+    want = np.zeros((1200, nb), dtype=np.complex64)
+    T.r2c(xb.cpu().numpy(), want, [1], True, 1.0)
+    check(Xb.cpu().numpy(), want, np.float32, n, "r2c batch of 1200 long lines")
     yb = torch.empty_like(xb)
     R.c2r(Xb, yb, [1], False, 1.0 / n)
     err = float(torch.linalg.vector_norm((yb - xb).double()) / torch.linalg.vector_norm(xb.double()))
@@ -552,7 +645,7 @@ def test_long_real_lines_two_transforms_per_thread(R):
 
 def test_fused_fourstep_long_strided_lines(R):
     """16384-point complex64 lines along a strided axis of arrays larger than the L2 cache: both four-step passes run
-    in one persistent kernel with the intermediate in an L2-resident scratch ring (pow2_fused4_kernel.cuh).  Widths that
+    in one persistent kernel with the intermediate in an L2-resident scratch ring (fused4v2_kernel.cuh, pow2_fused4_kernel.cuh).  Widths that
     are not multiples of the strip / tile width, a batch of arrays, in place and out of place, both directions,
     fct != 1 -- against the reference on the host."""
     import torch
@@ -561,11 +654,14 @@ def test_fused_fourstep_long_strided_lines(R):
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(12)
     n = 16384
-    os.environ["RFB200_FUSE4"] = "1"  # opt-in path (read per call); the same cases without it run in the last loop
+    # RFB200_FUSE4 (read per call): 2 = warp-specialised fused kernel (default), 1 = round-1 fused kernel, 0 = two launches
     os.environ["RFB200_FUSE4_CHECK"] = "1"
     try:
-        _fused_fourstep_cases(R, T, dev, rng, n)
-        assert R.launch_count() > 0
+        for mode in ("2", "1", "0"):
+            os.environ["RFB200_FUSE4"] = mode
+            R.launch_count_reset()
+            _fused_fourstep_cases(R, T, dev, rng, n)
+            assert R.launch_count() > 0
     finally:
         os.environ.pop("RFB200_FUSE4", None)
     _fused_fourstep_cases(R, T, dev, rng, n)
@@ -660,6 +756,7 @@ def test_long_complex_lines_two_transforms_per_thread(R):
     x = torch.from_numpy(cplx(rng, (2000, 8192), np.complex64)).to(dev)
     y = torch.empty_like(x)
     R.c2c(x, y, [1], True, 1.0)
-    ref = torch.fft.fft(x, dim=1)
-    err = float(torch.linalg.vector_norm((y - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128)))
-    assert err < parity.tol(np.float32, 8192), err
+    xh = x.cpu().numpy()
+    want = np.empty_like(xh)
+    T.c2c(xh, want, [1], True, 1.0)
+    check(y.cpu().numpy(), want, np.float32, 8192, "c2c batch of 2000 lines of 8192")

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round 2, session b: first run of the warp-specialised fused four-step kernel (fused4v2): parity, then timing sweeps.
+set -u
+O=gpurun_out
+mkdir -p $O
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "fused_fourstep or strided_lines" 2>&1 | tail -15 | tee $O/r2b_parity.log
+for cfg in "RFB200_FUSE4=0" "RFB200_FUSE4=2" "RFB200_FUSE4=2 RFB200_FUSE4_STAGES=3" "RFB200_FUSE4=2 RFB200_FUSE4_RING=14 RFB200_FUSE4_LAG=8" \
+           "RFB200_FUSE4=2 RFB200_FUSE4_RING=6 RFB200_FUSE4_LAG=3" "RFB200_FUSE4=2 RFB200_FUSE4_CTAS=2" "RFB200_FUSE4=2 RFB200_FUSE4_STAGES=3 RFB200_FUSE4_RING=14 RFB200_FUSE4_LAG=8"; do
+  echo "-- $cfg"
+  env $cfg timeout 120 python tools/microbench.py cfg2 2>&1 | grep -v "cuFFT\|^rocketfft"
+done 2>&1 | tee $O/r2b_sweep.log

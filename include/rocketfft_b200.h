@@ -175,6 +175,20 @@ const char *rfb200_launch_trace_get(void);
 /* DST-II/III with ortho=true: 1 (default) reproduces the reference, which scales element
  * 0 (H:3033-3039, README.md:61-65); 0 scales element N-1 as SciPy does. */
 void rfb200_set_dst_ortho_quirk(int enabled);
+/* Number of numba_* calls that failed since the library was loaded.  Those entry points return void (as the reference's
+ * do, _pocketfft_numba.cpp:31-223); a failed call prints its reason to stderr, leaves it readable through
+ * rfb200_last_error, fills a HOST output array with NaN (element by element), and increments this counter -- it never
+ * returns silently with an untouched output. */
+uint64_t rfb200_failure_count(void);
+/* Entries / bytes of the device table ("plan") cache.  Bounded: RFB200_PLAN_CACHE_ENTRIES (default 256) tables,
+ * RFB200_PLAN_CACHE_MB (default 1024) MiB; least recently used tables are released beyond that (reference: the 16-entry
+ * LRU plan cache, _pocketfft_hdronly.h:3169-3223). */
+void rfb200_plan_cache_stats(uint64_t *entries, uint64_t *bytes);
+/* numba_dst with an explicit choice of the DST-II/III scaling under ortho (quirk: 1 = the reference's, which scales
+ * element 0, _pocketfft_hdronly.h:3033-3039; 0 = SciPy's, element N-1), whatever rfb200_set_dst_ortho_quirk says.
+ * rfb200_dst takes the same choice in its `ortho` argument: 0 off, 1 on (process-wide choice), 2 on/SciPy, 3 on/reference. */
+void rfb200_host_dst(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
+                     rfb200_array_record *axes, uint64_t type, double fct, int ortho, int quirk);
 /* Host-side view of the tile order of the fused four-step kernel (pow2_fused4_kernel.cuh; test aid, no GPU needed):
  * unit `unit` of 2*nstrips -> (step << 32) | strip with step 0 = A, 1 = B; -1 past the end or if lag > nstrips. */
 int64_t rfb200_debug_fuse4_unit(uint32_t unit, uint32_t nstrips, uint32_t lag);
@@ -188,6 +202,11 @@ int rfb200_debug_tile_copy(const void *in, void *out, uint64_t rows, uint64_t co
  * smem_bytes of (unused) dynamic shared memory per CTA reproduce a transform kernel's occupancy. */
 int rfb200_debug_seg_copy(const void *in, void *out, uint32_t nrows, uint32_t seg_bytes, int64_t row_stride, uint32_t tiles0,
                           uint32_t tiles1, int64_t outer_stride, uint32_t threads, uint32_t smem_bytes, void *stream);
+/* Measurement aids of round 2 (csrc/probe.cu, tools/probe_l2_dsmem.py): sweep an L2-resident or DRAM-sized buffer (mode 0 read,
+ * 1 copy) `reps` times from `ctas` CTAs; exchange `kb` KiB with every other CTA of a thread-block cluster through distributed
+ * shared memory (mode 0 write, 1 read), cycles per CTA returned in `cycles`. */
+int rfb200_debug_l2_sweep(const void *in, void *out, uint64_t bytes, int reps, int mode, uint32_t ctas, void *sink, void *stream);
+int rfb200_debug_dsmem(uint32_t cluster, uint32_t nclusters, uint32_t kb, int reps, int mode, void *cycles, void *sink, void *stream);
 /* Library version string. */
 const char *rfb200_version(void);
 

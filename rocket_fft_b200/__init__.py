@@ -11,6 +11,7 @@ from .lowlevel import (  # noqa: F401
     c2r_pad,
     dct,
     dst,
+    failure_count,
     fftpack,
     genuine_hartley,
     good_size,
@@ -21,6 +22,7 @@ from .lowlevel import (  # noqa: F401
     launch_trace_get,
     lib,
     plan_cache_clear,
+    plan_cache_stats,
     r2c,
     r2c_pad,
     roll,

@@ -1,5 +1,7 @@
 // C ABI of librocketfft_b200.so: the ten numba_* drop-in symbols and the rfb200_* device entry
 // points declared in include/rocketfft_b200.h.
+#include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -34,17 +36,97 @@ cudaStream_t lib_stream() {
     return g_lib_stream[dev & 63];
 }
 
+// ---- process state: fork detection, failures of the void numba_* entry points --------------------------------------
+// A CUDA context does not survive fork() (the reference restarts its thread pool in the child, _pocketfft_hdronly.h:992-1006;
+// there is no such remedy for a GPU context): a child forked AFTER this library touched CUDA gets a clear error from every
+// transform instead of undefined behaviour.  A child forked before the first transform initialises CUDA itself and works.
+std::atomic<bool> g_cuda_used{false}, g_forked_child{false};
+std::atomic<uint64_t> g_failures{0};
+void on_fork_child() {
+    if (g_cuda_used.load()) {
+        g_forked_child.store(true);
+        plan_cache_forget();
+    }
+}
+struct ForkInit {
+    ForkInit() { pthread_atfork(nullptr, nullptr, on_fork_child); }
+} g_fork_init;
+
+// start of every transform entry point
+void enter_call() {
+    if (g_forked_child.load()) {
+        set_error("this process was forked after the parent had used CUDA, and a CUDA context does not survive fork(): start worker "
+                  "processes with the 'spawn' or 'forkserver' method, or fork before the first transform");
+        throw Error();
+    }
+    g_cuda_used.store(true);
+    check_async_error();
+}
+
+// Runs on the device that owns the arrays (not whatever device is current), restores the caller's device afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    static int device_of(const void *p) {
+        if (!p) return -1;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+        return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
+    }
+    DeviceGuard(const void *a, const void *b) {
+        const int da = device_of(a), db = device_of(b);
+        if (da >= 0 && db >= 0 && da != db) { set_error("input and output arrays live on different devices"); throw Error(); }
+        const int want = da >= 0 ? da : db;
+        if (want < 0) return;
+        RFB_CUDA_CHECK(cudaGetDevice(&prev));
+        if (prev != want) {
+            RFB_CUDA_CHECK(cudaSetDevice(want));
+            switched = true;
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// A numba_* entry point returns void: a failed call must not leave `aout` looking like a result.  Host output arrays are
+// filled with NaN (element by element: the gaps of a strided array are not ours), the message goes to stderr and stays
+// readable through rfb200_last_error, and rfb200_failure_count lets a caller detect failures after the fact.
+void fill_nan_host(const rfb200_array_record *aout, uint64_t ndim, const std::vector<int64_t> &shape, int64_t item, int64_t scalar) {
+    if (!aout || !aout->data) return;
+    for (auto v : shape) if (v <= 0) return;
+    std::vector<int64_t> idx(ndim, 0);
+    const int64_t *st = aout->shape_and_strides + ndim;
+    for (;;) {
+        int64_t off = 0;
+        for (uint64_t d = 0; d < ndim; ++d) off += idx[d] * st[d];
+        char *q = (char *)aout->data + off;
+        for (int64_t c = 0; c < item / scalar; ++c) {
+            if (scalar == 8) ((double *)q)[c] = NAN;
+            else ((float *)q)[c] = NAN;
+        }
+        uint64_t d = ndim;
+        while (d > 0) {
+            --d;
+            if (++idx[d] < shape[d]) break;
+            idx[d] = 0;
+            if (d == 0) return;
+        }
+        if (ndim == 0) return;
+    }
+}
+
 enum OpKind { OP_C2C, OP_R2C, OP_C2R, OP_C2C_SYM, OP_DCT, OP_DST, OP_FFTPACK, OP_SEP_HARTLEY, OP_GEN_HARTLEY };
 
 struct OpFlags {
     bool forward = true, ortho = false, r2h = false;
     int type = 2;
+    int quirk = -1;  // DST-II/III ortho scaling: -1 process default, 0 SciPy's, 1 the reference's
 };
 
 bool in_is_complex(OpKind k) { return k == OP_C2C || k == OP_C2R; }
 bool out_is_complex(OpKind k) { return k == OP_C2C || k == OP_R2C || k == OP_C2C_SYM; }
 
 void dispatch(OpKind k, const NdArgs &a, const OpFlags &f, cudaStream_t s) {
+    TableScope tables;  // the plan tables this call fetches stay leased until its kernels are enqueued
     for (auto ax : a.axes)
         if (ax >= a.shape.size()) { set_error("axis out of range"); throw Error(); }
     switch (k) {
@@ -53,7 +135,7 @@ void dispatch(OpKind k, const NdArgs &a, const OpFlags &f, cudaStream_t s) {
         case OP_C2R: op_c2r(a, f.forward, s); break;
         case OP_C2C_SYM: op_c2c_sym(a, f.forward, s); break;
         case OP_DCT: op_dcst(a, f.type, f.ortho, true, s); break;
-        case OP_DST: op_dcst(a, f.type, f.ortho, false, s); break;
+        case OP_DST: op_dcst(a, f.type, f.ortho, false, s, f.quirk); break;
         case OP_FFTPACK: op_fftpack(a, f.r2h, f.forward, s); break;
         case OP_SEP_HARTLEY: op_separable_hartley(a, s); break;
         case OP_GEN_HARTLEY: op_genuine_hartley(a, s); break;
@@ -79,6 +161,11 @@ bool is_device_ptr(const void *p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// One staging engine per device, created on first use with pageable memory; a call that finds it busy (another thread is
+// inside a host-array call on the same device) lets the driver stage its copies instead.
+std::mutex g_stager_mu[64];
+Stager *g_stager[64] = {nullptr};
+
 struct DevBuf {
     void *p = nullptr;
     cudaStream_t s;
@@ -90,7 +177,11 @@ struct DevBuf {
 void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout,
                    const rfb200_array_record *axes, double fct, const OpFlags &f) {
     clear_error();
+    std::vector<int64_t> fail_shape;  // output extents, known once the arguments are parsed (for the NaN fill on failure)
+    int64_t fail_item = 0, fail_scalar = 4;
+    bool out_on_host = false;
     try {
+        enter_call();
         NdArgs a;
         const rfb200_array_record *shp_src = (k == OP_C2R) ? aout : ain;
         a.shape.assign(shp_src->shape_and_strides, shp_src->shape_and_strides + ndim);
@@ -114,15 +205,26 @@ void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb2
         if (k == OP_R2C) shape_out[L] = a.shape[L] / 2 + 1;
         if (k == OP_C2R) shape_in[L] = a.shape[L] / 2 + 1;
 
-        cudaStream_t s = lib_stream();
+        fail_shape = shape_out;
+        fail_item = out_item;
+        fail_scalar = ssz;
         const bool dev_in = is_device_ptr(ain->data), dev_out = is_device_ptr(aout->data);
+        out_on_host = !dev_out;
         if (dev_in != dev_out) { set_error("input and output must both be host or both be device arrays"); throw Error(); }
         if (dev_in) {
+            // Device (or managed) memory behind a numba_* call: the reference's entry points are synchronous, so is this
+            // one.  Unless the caller chose a stream (rfb200_set_stream), the work goes to the legacy default stream, which
+            // orders it after the kernels the caller has queued on blocking streams, and the call returns when it is done.
+            DeviceGuard dg(ain->data, aout->data);
+            cudaStream_t ds = g_user_stream_set ? g_user_stream : (cudaStream_t) nullptr;
             a.in = (const char *)ain->data;
             a.out = (char *)aout->data;
-            dispatch(k, a, f, s);
+            dispatch(k, a, f, ds);
+            RFB_CUDA_CHECK(cudaStreamSynchronize(ds));
+            check_async_error();
             return;
         }
+        cudaStream_t s = lib_stream();
         // ---- host arrays: H2D -> kernels -> D2H, synchronous for the caller ----
         // Batched work (an untransformed outer dim whose slices are disjoint in memory) is cut into
         // chunks that go round-robin over three streams, so that the H2D copy of one chunk, the kernels
@@ -167,6 +269,19 @@ void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb2
         }
         const char *hin0 = (const char *)ain->data;
         char *hout0 = (char *)aout->data;
+        // pageable host memory (a plain NumPy array): our own staging ring instead of the driver's (staging.cu)
+        Stager *stg = nullptr;
+        std::unique_lock<std::mutex> stg_lock;
+        if (total_bytes >= (8ull << 20) && (host_memory_is_pageable(hin0) || host_memory_is_pageable(hout0))) {
+            int dev = 0;
+            RFB_CUDA_CHECK(cudaGetDevice(&dev));
+            stg_lock = std::unique_lock<std::mutex>(g_stager_mu[dev & 63], std::try_to_lock);
+            if (stg_lock.owns_lock()) {
+                if (!g_stager[dev & 63]) g_stager[dev & 63] = new Stager();
+                stg = g_stager[dev & 63];
+            }
+        }
+        const bool stage_in = stg && host_memory_is_pageable(hin0), stage_out = stg && host_memory_is_pageable(hout0);
         std::vector<DevBuf *> bufs;
         struct G { std::vector<DevBuf *> &v; ~G() { for (auto p : v) delete p; } } guard{bufs};
         const int64_t ext = cd < a.shape.size() ? a.shape[cd] : 1;
@@ -194,7 +309,8 @@ void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb2
             const bool same = (hin == hout) && (ibytes == obytes);
             DevBuf *din = new DevBuf(ibytes, cs);
             bufs.push_back(din);
-            RFB_CUDA_CHECK(cudaMemcpyAsync(din->p, hin, ibytes, cudaMemcpyHostToDevice, cs));
+            if (stage_in) stg->upload((char *)din->p, hin, ibytes, cs);
+            else RFB_CUDA_CHECK(cudaMemcpyAsync(din->p, hin, ibytes, cudaMemcpyHostToDevice, cs));
             char *dout_base;
             if (same) dout_base = (char *)din->p;
             else {
@@ -203,21 +319,29 @@ void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb2
                 dout_base = (char *)dout->p;
                 uint64_t dense = (uint64_t)out_item;
                 for (auto v : so) dense *= (uint64_t)v;
-                if (dense != obytes)  // gaps between elements must survive the round trip
-                    RFB_CUDA_CHECK(cudaMemcpyAsync(dout_base, hout, obytes, cudaMemcpyHostToDevice, cs));
+                if (dense != obytes) {  // gaps between elements must survive the round trip
+                    if (stage_out) stg->upload(dout_base, hout, obytes, cs);
+                    else RFB_CUDA_CHECK(cudaMemcpyAsync(dout_base, hout, obytes, cudaMemcpyHostToDevice, cs));
+                }
             }
             sub.in = (const char *)din->p - ilo;
             sub.out = dout_base - olo;
             dispatch(k, sub, f, cs);
-            RFB_CUDA_CHECK(cudaMemcpyAsync(hout, dout_base, obytes, cudaMemcpyDeviceToHost, cs));
+            if (stage_out) stg->download(hout, dout_base, obytes, cs);
+            else RFB_CUDA_CHECK(cudaMemcpyAsync(hout, dout_base, obytes, cudaMemcpyDeviceToHost, cs));
         }
         for (int i = 0; i < (nchunks > 1 ? 3 : 1); ++i) RFB_CUDA_CHECK(cudaStreamSynchronize(streams[i]));
+        if (stg) stg->finish();
+        check_async_error();
+        return;
     } catch (const Error &) {
-        fprintf(stderr, "rocketfft_b200: %s\n", last_error());
     } catch (const std::exception &e) {
         set_error(e.what());
-        fprintf(stderr, "rocketfft_b200: %s\n", e.what());
     }
+    // ---- failure: never return silently with an untouched output -----------------------------------------------------
+    g_failures.fetch_add(1);
+    fprintf(stderr, "rocketfft_b200: transform failed: %s\n", last_error());
+    if (out_on_host && fail_item) fill_nan_host(aout, ndim, fail_shape, fail_item, fail_scalar);
 }
 
 int run_device_op(OpKind k, int precision, size_t ndim, const int64_t *shape, const int64_t *stride_in,
@@ -225,6 +349,8 @@ int run_device_op(OpKind k, int precision, size_t ndim, const int64_t *shape, co
                   void *d_out, void *stream, const OpFlags &f) {
     clear_error();
     try {
+        enter_call();
+        DeviceGuard dg(d_in, d_out);
         NdArgs a;
         a.prec = precision ? 1 : 0;
         a.shape.assign(shape, shape + ndim);
@@ -317,7 +443,12 @@ RFB_EXPORT int rfb200_dct(DEV_ARGS, int type, double fct, int ortho, const void 
     return run_device_op(OP_DCT, DEV_PASS, fct, d_in, d_out, stream, mk_flags(true, type, ortho != 0));
 }
 RFB_EXPORT int rfb200_dst(DEV_ARGS, int type, double fct, int ortho, const void *d_in, void *d_out, void *stream) {
-    return run_device_op(OP_DST, DEV_PASS, fct, d_in, d_out, stream, mk_flags(true, type, ortho != 0));
+    // ortho: 0 = off, 1 = on with the process-wide DST-II/III scaling choice (default: the reference's quirk),
+    // 2 = on with SciPy's scaling, 3 = on with the reference's, whatever the process-wide setting is
+    OpFlags f = mk_flags(true, type, ortho != 0);
+    if (ortho == 2) f.quirk = 0;
+    if (ortho == 3) f.quirk = 1;
+    return run_device_op(OP_DST, DEV_PASS, fct, d_in, d_out, stream, f);
 }
 RFB_EXPORT int rfb200_r2r_fftpack(DEV_ARGS, int real2hermitian, int forward, double fct, const void *d_in,
                                   void *d_out, void *stream) {
@@ -335,6 +466,9 @@ RFB_EXPORT int rfb200_c2c_scatter(int precision, size_t ndim, const int64_t *sha
                                   size_t nparts, void *const *d_out_parts, void *stream) {
     clear_error();
     try {
+        enter_call();
+        DeviceGuard dg(d_in, nullptr);  // (the parts may be peer-mapped memory of other devices)
+        TableScope tables;
         NdArgs a;
         a.prec = precision ? 1 : 0;
         a.shape.assign(shape, shape + ndim);
@@ -362,6 +496,9 @@ static int run_pad_op(int kind, int precision, size_t ndim, const int64_t *shape
                       double fct, const void *d_in, void *d_out, void *stream) {
     clear_error();
     try {
+        enter_call();
+        DeviceGuard dg(d_in, d_out);
+        TableScope tables;
         NdArgs a;
         a.prec = precision ? 1 : 0;
         a.shape.assign(shape, shape + ndim);
@@ -399,6 +536,8 @@ RFB_EXPORT int rfb200_roll(int itemsize, size_t ndim, const int64_t *shape, cons
                            const int64_t *stride_out, const int64_t *shift, const void *d_in, void *d_out, void *stream) {
     clear_error();
     try {
+        enter_call();
+        DeviceGuard dg(d_in, d_out);
         op_roll(itemsize, std::vector<int64_t>(shape, shape + ndim), std::vector<int64_t>(stride_in, stride_in + ndim),
                 std::vector<int64_t>(stride_out, stride_out + ndim), std::vector<int64_t>(shift, shift + ndim),
                 (const char *)d_in, (char *)d_out, (cudaStream_t)stream);
@@ -415,6 +554,8 @@ RFB_EXPORT int rfb200_scale_lines(int precision, int complex_items, uint64_t nli
                                   void *d_data, void *stream) {
     clear_error();
     try {
+        enter_call();
+        DeviceGuard dg(d_table, d_data);
         op_scale_lines(precision ? 1 : 0, complex_items != 0, nlines, n, d_table, d_data, (cudaStream_t)stream);
         return 0;
     } catch (const Error &) {
@@ -443,6 +584,15 @@ RFB_EXPORT const char *rfb200_launch_trace_get(void) {
 }
 RFB_EXPORT void rfb200_launch_count_reset(void) { rfb::launch_count_reset(); }
 RFB_EXPORT void rfb200_set_dst_ortho_quirk(int enabled) { rfb::set_dst_ortho_quirk(enabled != 0); }
+RFB_EXPORT uint64_t rfb200_failure_count(void) { return g_failures.load(); }
+RFB_EXPORT void rfb200_plan_cache_stats(uint64_t *entries, uint64_t *bytes) { rfb::plan_cache_stats(entries, bytes); }
+// host-array variant of numba_dst with an explicit DST-II/III ortho scaling (quirk: 0 SciPy's, 1 the reference's)
+RFB_EXPORT void rfb200_host_dst(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout, rfb200_array_record *axes,
+                                uint64_t type, double fct, int ortho, int quirk) {
+    OpFlags f = mk_flags(true, (int)type, ortho != 0);
+    f.quirk = quirk ? 1 : 0;
+    run_record_op(OP_DST, ndim, ain, aout, axes, fct, f);
+}
 RFB_EXPORT int64_t rfb200_debug_fuse4_unit(uint32_t unit, uint32_t nstrips, uint32_t lag) {
     bool stepB = false;
     uint32_t strip = 0;

@@ -71,8 +71,6 @@ static void init_pool_once() {
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(mu);
     if (dev < 64 && !done[dev]) {
-        const int l2g = env_int("RFB200_L2_FETCH", 0);
-        if (l2g > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2g);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t thr = UINT64_MAX;
@@ -262,7 +260,7 @@ static bool plan_tile(const LineJob &job, const std::vector<Dim> &dims, TilePlan
     if (n > (1u << 20)) return false;
     tp.sched = radix_schedule(n, RMAX_GENERIC);  // n == 1: a single radix-1 pass
     if (tp.sched.empty() || tp.sched.size() > (size_t)MAXP) return false;
-    tp.padsh = (uint32_t)env_int("RFB200_PADSH", job.prec ? 4 : 5);
+    tp.padsh = job.prec ? 4 : 5;
     uint32_t pitch = (uint32_t)((n - 1) + ((n - 1) >> tp.padsh) + 1);
     pitch |= 1u;
     tp.pitch = pitch;
@@ -428,6 +426,18 @@ bool run_lines_pow2(const LineJob &job_in, cudaStream_t s) {
     return pow2_try(job, dims, s);
 }
 
+bool run_lines_tile(const LineJob &job_in, cudaStream_t s) {
+    init_pool_once();
+    LineJob job = job_in;
+    std::vector<Dim> dims;
+    if (!normalise(job, dims)) return true;
+    if (dims.size() > (size_t)MAXB) return false;
+    TilePlan tp;
+    if (!plan_tile(job, dims, tp)) return false;
+    launch_tile(job, dims, tp, s);
+    return true;
+}
+
 // dims: extent > 1, sorted by stride (dims[0] = the tile dim)
 static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
     // more batch dims than one launch takes: peel the outermost ones on the host
@@ -457,7 +467,7 @@ static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStrea
     }
     if (job.conv) { set_error("internal: convolution rows need the power-of-two kernel"); throw Error(); }
     if (!job.split_out.empty()) {
-        set_error("scatter output needs a power-of-two axis length between 16 and 16384 and aligned arrays");
+        set_error("scatter output needs aligned arrays and a power-of-two axis length: 16..16384 for contiguous lines, 16..2048 for strided ones");
         throw Error();
     }
     // smooth non-power-of-two lines: register-resident mixed-radix kernel
@@ -543,95 +553,14 @@ static void run_via_scratch(const LineJob &job, const std::vector<Dim> &dims, cu
 
 static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 
-// Long strided lines whose intermediate would not fit the L2 cache: both steps in ONE persistent kernel, the
-// intermediate of a strip of neighbouring lines in a ring of L2-resident scratch slots (pow2_fused4_kernel.cuh).
-// Knobs: RFB200_FUSE4 (1: on), RFB200_FUSE4_COLS (lines per strip), RFB200_FUSE4_RING, RFB200_FUSE4_LAG,
-// RFB200_FUSE4_MIN_MB (smallest array that takes this path), RFB200_FUSE4_CHECK (1: synchronise and check).
-static bool fourstep_fused(const LineJob &job, const std::vector<Dim> &dims, uint64_t n1, uint64_t n2, cudaStream_t s) {
-    // Off by default.  Measured on B200 (16384 x 8193 complex64 columns, profiles/r01c_*): the ring does stay in L2 (DRAM
-    // traffic 2.37 GB instead of 4.3 GB) but the column transform takes 0.90-0.97 ms against 0.82 ms for the two launches:
-    // the 128-point line-fast tiles are limited by instruction issue and load latency on the SM, not by DRAM, so halving
-    // the DRAM traffic buys nothing until the tile body itself is leaner.  (Read per call so that tests can switch it.)
-    const char *on_env = getenv("RFB200_FUSE4");
-    const int on = on_env ? atoi(on_env) : 2;
-    if (on != 1 || job.prec != 0 || n1 != n2 || n1 != 128) return false;
-    if (job.load_mode != LD_C2C || job.store_mode != ST_C2C || job.flags || (job.n_in && job.n_in != job.n) || job.twN ||
-        job.pre_tab || job.post_tab || !job.split_out.empty() || job.conv)
-        return false;
-    if (dims.empty() || dims.size() > 2 || !alignment_ok(job, dims)) return false;
-    const int64_t esz = 8;
-    if (dims[0].is != esz || dims[0].os != esz || iabs64(job.is) <= esz || iabs64(job.os) <= esz) return false;
-    static const int cw_env = env_int("RFB200_FUSE4_COLS", 64);
-    const int64_t CW = std::max(32, (cw_env / 32) * 32);
-    const int64_t cols = dims[0].n, nstr = (cols + CW - 1) / CW, outer = dims.size() == 2 ? dims[1].n : 1;
-    if (cols < CW) return false;
-    // smaller arrays: the two-launch path keeps its intermediate in L2 by itself
-    static const int min_mb = env_int("RFB200_FUSE4_MIN_MB", 96);
-    if ((uint64_t)cols * job.n * (uint64_t)esz < ((uint64_t)min_mb << 20)) return false;
-    const uint64_t S = (uint64_t)outer * (uint64_t)nstr;
-    if (S >= (1u << 20)) return false;
-    static const int ring_env = env_int("RFB200_FUSE4_RING", 4), lag_env = env_int("RFB200_FUSE4_LAG", 2);
-    Fuse4Ctl c;
-    memset(&c, 0, sizeof(c));
-    c.nstrips = (uint32_t)S;
-    c.cols = (uint32_t)cols;
-    c.cw = (uint32_t)CW;
-    c.lag = (uint32_t)std::min<uint64_t>((uint64_t)std::max(lag_env, 1), S);
-    c.ring = (uint32_t)std::max<int64_t>(ring_env, (int64_t)c.lag + 1);
-    c.tiles = (uint32_t)((CW / 32) * (int64_t)n2);
-    c.d_spo = make_fastdiv((uint32_t)nstr);
-    c.in_outer = dims.size() == 2 ? dims[1].is : 0;
-    c.out_outer = dims.size() == 2 ? dims[1].os : 0;
-    c.in_strip = c.out_strip = CW * esz;
-    c.slot_bytes = (int64_t)job.n * CW * esz;
-    const size_t ring_bytes = (size_t)c.ring * (size_t)c.slot_bytes, ctr_bytes = (2 * S + 2) * sizeof(uint32_t);
-    Scratch sc(ring_bytes + ctr_bytes, s);
-    c.ctr = (uint32_t *)((char *)sc.p + ring_bytes);
-    const int64_t s_axis = CW * esz;  // one row of the strip's intermediate: CW neighbouring lines
-    // A: for every residue j0 (mod n2) an n1-point DFT over j1 of x[j1*n2 + j0], times exp(-2 pi i j0 k1 / n),
-    //    stored at slot[k1*n2 + j0][line];  B: for every k1 an n2-point DFT over j0 -> X[k2*n1 + k1]
-    LineJob A, B;
-    A.prec = B.prec = job.prec;
-    A.backward = B.backward = job.backward;
-    A.n = n1;
-    A.is = (int64_t)n2 * job.is;
-    A.os = (int64_t)n2 * s_axis;
-    A.batch = {Dim{CW, esz, esz, false}, Dim{(int64_t)n2, job.is, s_axis, true}};
-    A.in = job.in;
-    A.out = (char *)sc.p;
-    A.fct = 1.0;
-    A.twN = job.n;
-    B.n = n2;
-    B.is = s_axis;
-    B.os = (int64_t)n1 * job.os;
-    B.batch = {Dim{CW, esz, esz, false}, Dim{(int64_t)n1, (int64_t)n2 * s_axis, job.os, false}};
-    B.in = (const char *)sc.p;
-    B.out = job.out;
-    B.fct = job.fct;
-    std::vector<Dim> dA, dB;
-    if (!normalise(A, dA) || !normalise(B, dB)) return false;
-    if (dA.size() != 2 || dB.size() != 2 || dA[0].n != CW || dB[0].n != CW) return false;
-    RFB_CUDA_CHECK(cudaMemsetAsync(c.ctr, 0, ctr_bytes, s));
-    if (!launch_fourstep_fused_f32(A, dA, B, dB, c, s)) return false;
-    static const int check = env_int("RFB200_FUSE4_CHECK", 0);
-    if (check) {
-        // debugging aid: a dependency that was never satisfied shows up as ctr[1] != 0 (the kernel does not hang)
-        uint32_t flag = 0;
-        RFB_CUDA_CHECK(cudaMemcpyAsync(&flag, c.ctr + 1, sizeof(flag), cudaMemcpyDeviceToHost, s));
-        RFB_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (flag) { set_error("fused four-step: a tile waited for a dependency that never completed"); throw Error(); }
-    }
-    return true;
-}
-
 static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
     uint64_t n1, n2;
     choose_split(job.n, job.prec, n1, n2);
-    // RFB200_FUSE4: 0 = two launches, 1 = the ticket-per-CTA fused kernel of round 1, 2 (default) = the warp-specialised
-    // fused kernel fed by the copy engine (fused4v2_kernel.cuh).  Read per call so that tests can switch it.
+    // Long strided complex64 lines of arrays beyond the L2 cache: both steps in ONE warp-specialised persistent kernel fed by
+    // the copy engine, the intermediate in an L2-resident ring (fused4v2_kernel.cuh).  RFB200_FUSE4=0 (read per call, so that
+    // tests can compare the paths) forces the two-launch form.
     const char *f4 = getenv("RFB200_FUSE4");
-    if ((!f4 || atoi(f4) >= 2) && launch_fourstep_fused2_f32(job, dims, s)) return;
-    if (fourstep_fused(job, dims, n1, n2, s)) return;
+    if ((!f4 || atoi(f4) != 0) && launch_fourstep_fused2_f32(job, dims, s)) return;
     run_fourstep_plain(job, dims, s);
 }
 
@@ -721,18 +650,24 @@ static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cuda
         void *w = nullptr;
         bhat = get_table(TAB_CHIRP_FFT, job.prec, n, M, &created, &w);
         if (created) {
-            dim3 grid((unsigned)((M + 255) / 256));
-            if (job.prec) blue_kernel_seq<double><<<grid, 256, 0, s>>>((double2 *)w, (uint32_t)n, (uint32_t)M, (const double2 *)chirp);
-            else blue_kernel_seq<float><<<grid, 256, 0, s>>>((float2 *)w, (uint32_t)n, (uint32_t)M, (const float2 *)chirp);
-            RFB_AFTER_LAUNCH();
-            LineJob f;
-            f.prec = job.prec;
-            f.n = M;
-            f.is = f.os = (int64_t)esz;
-            f.in = (const char *)w;
-            f.out = (char *)w;
-            run_lines(f, s);
-            RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+            // the table's contents are computed here; if that fails the (unfilled) entry must not stay in the cache
+            try {
+                dim3 grid((unsigned)((M + 255) / 256));
+                if (job.prec) blue_kernel_seq<double><<<grid, 256, 0, s>>>((double2 *)w, (uint32_t)n, (uint32_t)M, (const double2 *)chirp);
+                else blue_kernel_seq<float><<<grid, 256, 0, s>>>((float2 *)w, (uint32_t)n, (uint32_t)M, (const float2 *)chirp);
+                RFB_AFTER_LAUNCH();
+                LineJob f;
+                f.prec = job.prec;
+                f.n = M;
+                f.is = f.os = (int64_t)esz;
+                f.in = (const char *)w;
+                f.out = (char *)w;
+                run_lines(f, s);
+                RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+            } catch (...) {
+                discard_table(TAB_CHIRP_FFT, job.prec, n, M);
+                throw;
+            }
         }
     }
     // ---- fused pipeline: two FFT_M jobs, chirp / padding / spectrum multiply / truncation ride on
@@ -750,8 +685,7 @@ static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cuda
             if (!lf && M > (1ull << 14) && job.is == (int64_t)esz && job.os == (int64_t)esz) {
                 // rows of n2 = 4096 points (the contiguous kernel's sweet spot), columns of n1 = M / n2 >= 16 points:
                 // short columns mean wide tiles (many neighbouring columns per CTA) for the strided passes
-                static const int log_n2 = env_int("RFB200_BLUE_LOGN2", 12);
-                int l2 = std::min(std::max(log_n2, 8), 13);
+                int l2 = 12;
                 while (logM - l2 < 4) --l2;
                 while (logM - l2 > 11) ++l2;
                 n2 = 1ull << l2;
@@ -773,11 +707,16 @@ static void run_bluestein(const LineJob &job, const std::vector<Dim> &dims, cuda
                     void *w = nullptr;
                     bhat_t = get_table(TAB_CHIRP_FFT_T, job.prec, n, M, &created, &w);
                     if (created) {
-                        dim3 grid((unsigned)((M + 255) / 256));
-                        if (job.prec) table_to_fourstep_order<double><<<grid, 256, 0, s>>>((double2 *)w, (const double2 *)bhat, (uint32_t)n1, (uint32_t)n2);
-                        else table_to_fourstep_order<float><<<grid, 256, 0, s>>>((float2 *)w, (const float2 *)bhat, (uint32_t)n1, (uint32_t)n2);
-                        RFB_AFTER_LAUNCH();
-                        RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+                        try {
+                            dim3 grid((unsigned)((M + 255) / 256));
+                            if (job.prec) table_to_fourstep_order<double><<<grid, 256, 0, s>>>((double2 *)w, (const double2 *)bhat, (uint32_t)n1, (uint32_t)n2);
+                            else table_to_fourstep_order<float><<<grid, 256, 0, s>>>((float2 *)w, (const float2 *)bhat, (uint32_t)n1, (uint32_t)n2);
+                            RFB_AFTER_LAUNCH();
+                            RFB_CUDA_CHECK(cudaStreamSynchronize(s));
+                        } catch (...) {
+                            discard_table(TAB_CHIRP_FFT_T, job.prec, n, M);
+                            throw;
+                        }
                     }
                 }
                 std::vector<int64_t> st(dims.size());

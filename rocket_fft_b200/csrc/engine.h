@@ -46,11 +46,15 @@ struct LineJob {
     // circular-convolution line (power-of-two kernel only, contiguous lines): forward transform, times pre_tab[g]
     // with g indexed by the BIN, backward transform; twN / fct apply to the final store
     bool conv = false;
+    // tables of the DCT / DST load / store modes LD_G_* / ST_G_* (generic tile kernel only)
+    const void *aux_ld = nullptr, *aux_st = nullptr;
 };
 
 void run_lines(const LineJob &job, cudaStream_t stream);
 // Only the register-resident power-of-two kernel; false (nothing launched) if it does not take the job.
 bool run_lines_pow2(const LineJob &job, cudaStream_t stream);
+// Only the generic shared-memory tile kernel (one launch); false (nothing launched) if a line does not fit.
+bool run_lines_tile(const LineJob &job, cudaStream_t stream);
 
 // N-D array description as it arrives through the ABI.
 struct NdArgs {
@@ -76,7 +80,7 @@ void op_c2r_pad(const NdArgs &a, const std::vector<int64_t> &shape_in, bool forw
 // out[(i + shift) mod n] = in[i] along every dim (fftshift / ifftshift / roll); item: 4, 8 or 16 bytes
 void op_roll(int64_t item, const std::vector<int64_t> &shape, const std::vector<int64_t> &sin,
              const std::vector<int64_t> &sout, const std::vector<int64_t> &shift, const char *in, char *out, cudaStream_t s);
-void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s);
+void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s, int quirk_mode = -1);
 void op_fftpack(const NdArgs &a, bool r2h, bool forward, cudaStream_t s);
 void op_separable_hartley(const NdArgs &a, cudaStream_t s);
 void op_genuine_hartley(const NdArgs &a, cudaStream_t s);
@@ -91,6 +95,21 @@ void launch_trace_enable(bool on);
 std::string launch_trace_get();
 void launch_count_reset();
 void set_dst_ortho_quirk(bool on);
+
+// staged copies of pageable host memory (staging.cu)
+class Stager {
+  public:
+    Stager();
+    ~Stager();
+    void upload(char *dst_dev, const char *src_host, size_t n, cudaStream_t s);    // returns when the host data has been read
+    void download(char *dst_host, const char *src_dev, size_t n, cudaStream_t s);  // asynchronous: finish() waits for it
+    void finish();
+    struct Impl;
+
+  private:
+    Impl *impl_;
+};
+bool host_memory_is_pageable(const void *p);
 
 // stream-ordered scratch
 struct Scratch {

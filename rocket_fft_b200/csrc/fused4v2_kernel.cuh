@@ -8,8 +8,12 @@
 //   strip  = 32 neighbouring lines (columns); its intermediate, 16384 rows x 256 B = 4 MiB, lives in ring slot (strip % ring)
 //   A(s,j0): 128-point DFTs over the rows j1*128 + j0 of the strip, times w_16384^(j0 k1), stored to slot rows k1*128 + j0
 //   B(s,k1): 128-point DFTs over the slot rows k1*128 + j0 (one contiguous 32 KiB block), stored to array rows k2*128 + k1
-//   unit order (fuse4_decode_unit): A(0) .. A(lag-1) | A(lag) B(0) | A(lag+1) B(1) | ...; a unit has 128 tiles.
-//   B(s) needs all 128 tiles of A(s) (counter doneA[s]); A(s) needs the slot's previous tenant B(s - ring) read (doneB).
+//   G adjacent strips form a group; a unit = one step of one group = 128 x G tiles in the order (j0 or k1) major, strip
+//   minor, so that tiles in flight at the same time touch G x 256 contiguous bytes of every array row they share (DRAM page
+//   locality: measured 0.65 -> see DESIGN.md).  Unit order (fuse4_decode_unit over groups): A(0) .. A(lag-1) | A(lag) B(0) |
+//   A(lag+1) B(1) | ...  B(s) needs all 128 tiles of A(s) (counter doneA[s]); A(s) needs the slot's previous tenant
+//   B(s - ring) read (doneB); lag and ring count groups, strips are numbered group * G + g (numbers past the array's last
+//   strip are skipped).
 //
 // CTA = 4 transform warps + 1 copy warp, STAGES shared-memory stages of 34.25 KiB.  The copy warp draws tickets (an atomic
 // counter: tiles are handed out in unit order, so every tile a CTA waits for has been taken by a running CTA earlier --
@@ -41,18 +45,20 @@ struct F4v2Params {
     char *ring_mem;        // ring * 4 MiB of scratch
     uint32_t *ctr;         // [0] ticket, [1] error, [2 .. 2+S) doneA, [2+S .. 2+2S) doneB
     uint32_t *host_err;    // pinned, mapped: set when a dependency never completed
-    uint32_t nstrips, spo; // strips in total / per outer item
-    uint32_t ring, lag;
-    uint32_t total_items;  // 2 * nstrips * 128
+    uint32_t nstrips, spo; // strip numbers in total (ngroups * G) / real strips per outer item
+    uint32_t ngroups, gpo; // groups of G adjacent strips in total / per outer item
+    uint32_t glog;         // log2 G
+    uint32_t ring, lag;    // in groups; ring slots = ring * G
+    uint32_t total_items;  // 2 * ngroups * G * 128
     uint32_t mis_in[2], mis_out[2];  // per row-parity class: 1 if its rows start 8 bytes past a 16-byte boundary
-    FastDiv d_spo, d_ring;
+    FastDiv d_gpo, d_ring;  // group -> (outer, group in outer); strip number -> ring slot (mod ring * G)
     int backward;
     float fct;
     const float2 *stw;       // Stockham twiddles of the 128-point line transform
     const float2 *twA, *twB; // exp(-2 pi i t / 16384) = twA[t / S] * twB[t % S]
     FastDiv d_twS;
     uint32_t max_idle;       // bound on the copy thread's idle polls (never hang the GPU)
-    uint32_t pf_strips;      // L2 prefetch distance of the array-side loads, in strips (0: off)
+    uint32_t dbg_only;       // measurement aid: 1 = step A tiles only, 2 = step B tiles only (no dependencies; wrong results)
 };
 
 // tensor maps (kernel parameters): [0] / [1] input rows of even / odd parity, [2] / [3] output rows, [4] ring (A's store box)
@@ -70,6 +76,7 @@ constexpr int TILE_BYTES = N * ROW;
 constexpr int ROW_MIS = 272;                   // landing row of a misaligned class: 34 elements, the tile starts 8 bytes in
 constexpr uint32_t KIND_A = 0, KIND_B = 1, KIND_STOP = 2;
 constexpr uint32_t FLAG_SHIFT = 1, FLAG_STG = 2;  // tile landed 8 bytes into 272-byte rows / result stored from registers
+constexpr uint32_t FLAG_AREG = 4;                 // A tile stored to the ring from registers and published by the transform warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
@@ -135,6 +142,14 @@ __device__ __forceinline__ void red_release(uint32_t *p, uint32_t v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// strip number -> (outer item, strip within it); false for the numbers past the last strip of an outer item
+__device__ __forceinline__ bool decode_strip(const F4v2Params &p, uint32_t vs, uint32_t &outer, uint32_t &sw) {
+    uint32_t gin;
+    fdivmod(vs >> p.glog, p.d_gpo, outer, gin);
+    sw = (gin << p.glog) + (vs & ((1u << p.glog) - 1u));
+    return sw < p.spo;
+}
+
 using PL = P2<7>;  // 128 = 8 x 16: a radix-8 pass, one exchange, a radix-16 pass
 
 template <int P>
@@ -161,6 +176,7 @@ __device__ __forceinline__ void compute2(float2 *a, float2 *b, int t, const floa
 }
 
 // the transform warps' work on one tile: stage = 128 rows x 256 B in, the same out
+template <bool DBG_COPY>
 __device__ __forceinline__ void transform_tile(const F4v2Params &p, unsigned char *stage, uint64_t *ready_bar, uint32_t kind,
                                                uint32_t strip, uint32_t tile, uint32_t flags, int ctid) {
     const int wp = ctid & (WP - 1), t = ctid >> 4;  // pair of lines, butterfly
@@ -197,7 +213,7 @@ __device__ __forceinline__ void transform_tile(const F4v2Params &p, unsigned cha
             for (int i = 0; i < 16; ++i) { a[i] = cswap(a[i]); b[i] = cswap(b[i]); }
         }
     }
-    compute2<0>(a, b, t, p.stw);
+    if (!DBG_COPY) compute2<0>(a, b, t, p.stw);
     // ---- exchange through the stage (the tile is dead once every thread has read its elements) ------------------------------
     {
         float4 *line = reinterpret_cast<float4 *>(stage) + wp * XPITCH;
@@ -217,9 +233,10 @@ __device__ __forceinline__ void transform_tile(const F4v2Params &p, unsigned cha
             b[m] = make_float2(u.z, u.w);
         }
     }
-    compute2<1>(a, b, t, p.stw);
+    if (!DBG_COPY) compute2<1>(a, b, t, p.stw);
     // ---- thread t holds bins k = t + 8 q, q = 0..15, of both lines ------------------------------------------------------------
-    if (kind == KIND_A) {
+    if (DBG_COPY) {
+    } else if (kind == KIND_A) {
         // times exp(-2 pi i j0 k / 16384): exact two-level look-up for every 4th bin, recurrence in between
         const uint32_t c = tile;
         auto lookup = [&](uint32_t x) {
@@ -247,10 +264,11 @@ __device__ __forceinline__ void transform_tile(const F4v2Params &p, unsigned cha
         }
     }
     if (flags & FLAG_STG) {
-        // rows that are only 8-byte aligned: no TMA store; this thread is done with the stage
+        // B tiles leave from registers: nothing waits for these stores (no counter to publish), and the stage is free for the
+        // next load one staging pass + one copy-engine read-out earlier.  16-byte stores where the rows allow it.
         mbar_arrive(ready_bar);
         uint32_t outer, sw;
-        fdivmod(strip, p.d_spo, outer, sw);
+        decode_strip(p, strip, outer, sw);
         const uint32_t ext = min((uint32_t)W, p.cols - sw * (uint32_t)W);
         const bool ok0 = 2u * (uint32_t)wp < ext, ok1 = 2u * (uint32_t)wp + 1u < ext;
         if (!ok0) return;
@@ -258,11 +276,52 @@ __device__ __forceinline__ void transform_tile(const F4v2Params &p, unsigned cha
                   (int64_t)((uint32_t)t * (uint32_t)N + tile) * p.out_pitch;
         const int64_t step_q = (int64_t)(8 * N) * p.out_pitch;
         const uint64_t pol = l2_policy_stream();
+        if (ok1 && ((reinterpret_cast<uintptr_t>(o) | (uintptr_t)step_q) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(o), "f"(a[q].x), "f"(a[q].y),
+                             "f"(b[q].x), "f"(b[q].y), "l"(pol) : "memory");
+                o += step_q;
+            }
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             st_policy(reinterpret_cast<float2 *>(o), a[q], pol);
             if (ok1) st_policy(reinterpret_cast<float2 *>(o + 8), b[q], pol);
             o += step_q;
+        }
+        return;
+    }
+    if (flags & FLAG_AREG) {
+        // A tile to the ring from registers: the stage is free now; the tile is published (doneA) once every thread's stores
+        // are ordered before one thread's GPU-scope fence (barrier + fence: the grid-synchronisation pattern)
+        mbar_arrive(ready_bar);
+        uint32_t rq, slot;
+        fdivmod(strip, p.d_ring, rq, slot);
+        char *o = p.ring_mem + (int64_t)slot * ((int64_t)N * TILE_BYTES) + (int64_t)((uint32_t)t * (uint32_t)N + tile) * ROW;
+        const uint64_t pol = l2_policy_keep();
+        if (flags & FLAG_SHIFT) {
+            o += wp * 8;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                st_policy(reinterpret_cast<float2 *>(o), a[q], pol);
+                st_policy(reinterpret_cast<float2 *>(o + 128), b[q], pol);
+                o += 8 * N * ROW;
+            }
+        } else {
+            o += wp * 16;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(o), "f"(a[q].x), "f"(a[q].y),
+                             "f"(b[q].x), "f"(b[q].y), "l"(pol) : "memory");
+                o += 8 * N * ROW;
+            }
+        }
+        bar_compute();
+        if (ctid == 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            red_release(p.ctr + 2 + strip, 1u);
         }
         return;
     }
@@ -285,7 +344,7 @@ __device__ __forceinline__ void transform_tile(const F4v2Params &p, unsigned cha
 
 }  // namespace f4v2
 
-template <int STAGES>
+template <int STAGES, bool B_TMA_STORE, bool A_REG, bool DBG_COPY = false>
 __global__ void __launch_bounds__(f4v2::NTHREADS, STAGES == 2 ? 3 : 2)
     fft_fourstep_fused2_kernel(const F4v2Params p, const __grid_constant__ F4v2Maps maps) {
     using namespace f4v2;
@@ -307,7 +366,7 @@ __global__ void __launch_bounds__(f4v2::NTHREADS, STAGES == 2 ? 3 : 2)
             mbar_wait(full + b, par);
             const uint4 it = items[b];
             if (it.x == KIND_STOP) break;
-            transform_tile(p, stages + b * STAGE_BYTES, ready + b, it.x, it.y, it.z, it.w, threadIdx.x);
+            transform_tile<DBG_COPY>(p, stages + b * STAGE_BYTES, ready + b, it.x, it.y, it.z, it.w, threadIdx.x);
         }
         return;
     }
@@ -336,12 +395,30 @@ __global__ void __launch_bounds__(f4v2::NTHREADS, STAGES == 2 ? 3 : 2)
         if (!exhausted && !next_ok) {
             if (ticket >= p.total_items) exhausted = true;
             else {
-                fuse4_decode_unit(ticket >> 7, S, p.lag, nextB, next_strip);
-                next_tile = ticket & 127u;
+                // ticket -> (unit, tile-in-unit) -> (step, group) x (j0 or k1, strip in group)
+                const uint32_t within = ticket & ((128u << p.glog) - 1u);
+                uint32_t grp;
+                fuse4_decode_unit(ticket >> (7 + p.glog), p.ngroups, p.lag, nextB, grp);
+                if (p.dbg_only) { nextB = p.dbg_only == 2; grp = ticket >> (7 + p.glog); }
+                next_strip = (grp << p.glog) + (within & ((1u << p.glog) - 1u));
+                next_tile = within >> p.glog;
                 next_ok = true;
-                if (nextB && next_strip != readyA) {
+                uint32_t o_, s_;
+                if (!decode_strip(p, next_strip, o_, s_)) {  // past the last strip: nothing to do for this ticket
+                    ticket = atomicAdd(p.ctr, 1u);
+                    next_ok = false;
+                    continue;
+                }
+                if (nextB && next_strip != readyA && !p.dbg_only) {
                     next_ok = ld_acq(doneA + next_strip) >= (uint32_t)N;
                     if (next_ok) readyA = next_strip;
+                }
+                const uint32_t rs = p.ring << p.glog;
+                if (A_REG && next_ok && !nextB && next_strip >= rs && freeB != next_strip - rs && !p.dbg_only &&
+                    decode_strip(p, next_strip - rs, o_, s_)) {
+                    // the transform warps store this tile to the ring themselves: the slot must be free before the tile starts
+                    next_ok = ld_acq(doneB + (next_strip - rs)) >= (uint32_t)N;
+                    if (next_ok) freeB = next_strip - rs;
                 }
             }
         }
@@ -356,7 +433,7 @@ __global__ void __launch_bounds__(f4v2::NTHREADS, STAGES == 2 ? 3 : 2)
                     red_release(doneB + strip, 1u);  // the slot's rows of this tile were consumed when the tile landed
                     if (!(it.w & FLAG_STG)) {
                         uint32_t outer, sw;
-                        fdivmod(strip, p.d_spo, outer, sw);
+                        decode_strip(p, strip, outer, sw);
                         tma_store_4d(&maps.m[2 + (tile & 1u)], (int)(sw * W), (int)(tile >> 1), 0, (int)outer, src, pol_stream);
                         bulk_commit();
                         if (pending >= 0) { bulk_wait<1>(); publish_pending(); }
@@ -364,11 +441,16 @@ __global__ void __launch_bounds__(f4v2::NTHREADS, STAGES == 2 ? 3 : 2)
                     }
                     ++nret;
                     did = true;
+                } else if (A_REG) {
+                    ++nret;  // stored and published by the transform warps
+                    did = true;
                 } else {
                     bool ok = true;
-                    if (strip >= p.ring && !aborted && freeB != strip - p.ring) {
-                        ok = ld_acq(doneB + (strip - p.ring)) >= (uint32_t)N;
-                        if (ok) freeB = strip - p.ring;
+                    const uint32_t rs = p.ring << p.glog;  // ring slots
+                    uint32_t o_, s_;
+                    if (strip >= rs && !aborted && freeB != strip - rs && !p.dbg_only && decode_strip(p, strip - rs, o_, s_)) {
+                        ok = ld_acq(doneB + (strip - rs)) >= (uint32_t)N;
+                        if (ok) freeB = strip - rs;
                     }
                     if (ok) {
                         uint32_t rq, slot;
@@ -396,11 +478,12 @@ __global__ void __launch_bounds__(f4v2::NTHREADS, STAGES == 2 ? 3 : 2)
                 const uint32_t strip = next_strip, tile = next_tile, odd = tile & 1u;
                 unsigned char *dst = stages + b * STAGE_BYTES;
                 uint32_t outer, sw;
-                fdivmod(strip, p.d_spo, outer, sw);
+                decode_strip(p, strip, outer, sw);
                 uint32_t flags;
-                // TMA stores only for 16-byte aligned rows and full strips (a store box must not reach past the strip)
-                if (nextB) flags = (p.mis_out[odd] || (sw + 1u) * (uint32_t)W > p.cols) ? FLAG_STG : 0u;
-                else flags = p.mis_in[odd] ? FLAG_SHIFT : 0u;
+                // B_TMA_STORE: B tiles of 16-byte aligned rows and full strips staged and stored by the copy engine (a store
+                // box must not reach past the strip); default: every B tile is stored from registers
+                if (nextB) flags = (!B_TMA_STORE || p.mis_out[odd] || (sw + 1u) * (uint32_t)W > p.cols) ? FLAG_STG : 0u;
+                else flags = (p.mis_in[odd] ? FLAG_SHIFT : 0u) | (A_REG ? FLAG_AREG : 0u);
                 items[b] = make_uint4(nextB ? KIND_B : KIND_A, strip, tile, flags);
                 mbar_arrive_tx(full + b, (flags & FLAG_SHIFT) ? (uint32_t)(N * ROW_MIS) : (uint32_t)TILE_BYTES);
                 if (nextB) {
@@ -411,13 +494,6 @@ __global__ void __launch_bounds__(f4v2::NTHREADS, STAGES == 2 ? 3 : 2)
                 } else {
                     // (a misaligned class: the map starts 8 bytes early and its box is 34 wide, so x = sw * W is aligned)
                     tma_load_4d(dst, &maps.m[odd], (int)(sw * W), (int)(tile >> 1), 0, (int)outer, full + b, pol_stream);
-                    // the same tile of a later strip: DRAM -> L2 now, so that its load finds it there
-                    const uint32_t ps = strip + p.pf_strips;
-                    if (p.pf_strips && ps < S) {
-                        uint32_t po, psw;
-                        fdivmod(ps, p.d_spo, po, psw);
-                        tma_prefetch_4d(&maps.m[odd], (int)(psw * W), (int)(tile >> 1), 0, (int)po);
-                    }
                 }
                 ++nload;
                 ticket = atomicAdd(p.ctr, 1u);

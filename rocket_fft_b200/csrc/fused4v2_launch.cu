@@ -68,9 +68,9 @@ static bool make_map(CUtensorMap *m, const void *base, uint64_t nx, uint64_t ny,
               CU_TENSOR_MAP_SWIZZLE_NONE, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int STAGES>
+template <int STAGES, bool B_TMA_STORE, bool A_REG, bool DBG_COPY = false>
 static bool launch_f4v2(const F4v2Params &p, const F4v2Maps &maps, cudaStream_t s) {
-    auto kern = fft_fourstep_fused2_kernel<STAGES>;
+    auto kern = fft_fourstep_fused2_kernel<STAGES, B_TMA_STORE, A_REG, DBG_COPY>;
     const size_t smem = (size_t)STAGES * f4v2::STAGE_BYTES + (size_t)STAGES * 32;
     static thread_local int dev_set = -1;
     static thread_local int per_sm = 0, sms = 0;
@@ -83,9 +83,7 @@ static bool launch_f4v2(const F4v2Params &p, const F4v2Maps &maps, cudaStream_t 
         dev_set = dev;
     }
     if (per_sm < 1) return false;
-    static const int cap = env_i("RFB200_FUSE4_CTAS", 0);  // CTAs per SM (0: what fits)
-    const int use = cap > 0 ? std::min(cap, per_sm) : per_sm;
-    const unsigned grid = (unsigned)std::min<uint64_t>(p.total_items, (uint64_t)sms * (uint64_t)use);
+    const unsigned grid = (unsigned)std::min<uint64_t>(p.total_items, (uint64_t)sms * (uint64_t)per_sm);
     kern<<<grid, f4v2::NTHREADS, smem, s>>>(p, maps);
     count_launch(STAGES == 2 ? "fft_fourstep_fused2_kernel<2>" : "fft_fourstep_fused2_kernel<3>");
     RFB_CUDA_CHECK(cudaGetLastError());
@@ -116,20 +114,31 @@ bool launch_fourstep_fused2_f32(const LineJob &job, const std::vector<Dim> &dims
     static const int min_mb = env_i("RFB200_FUSE4_MIN_MB", 64);
     if ((uint64_t)cols * (uint64_t)outer * job.n * (uint64_t)esz < ((uint64_t)min_mb << 20) || cols < 32) return false;
     const int64_t spo = (cols + 31) / 32;
-    const uint64_t S = (uint64_t)outer * (uint64_t)spo;
+    // Strips per group (see the kernel's header): 1.  Measured on B200 (profiles/r02h_fuse4v2_strip_groups.log): grouping 2 / 4 / 8
+    // adjacent strips in the tile order -- more contiguous bytes per array row in flight -- is slower (0.67 / 0.73 / 0.79 ms
+    // against 0.67 ms): the copy engine's 256-byte row requests spread best over the L2 slices when they are scattered.
+    const int glog = 0;
+    const int64_t G = 1ll << glog;
+    const int64_t gpo = (spo + G - 1) / G;
+    const uint64_t ngroups = (uint64_t)outer * (uint64_t)gpo, S = ngroups * (uint64_t)G;
     if (S >= (1u << 22) || (uint64_t)(16384 * job.is) >= (1ull << 40) || (uint64_t)in_outer >= (1ull << 40) ||
         (uint64_t)out_outer >= (1ull << 40))
         return false;
-    static const int ring_env = env_i("RFB200_FUSE4_RING", 10), lag_env = env_i("RFB200_FUSE4_LAG", 6);
+    // 6 strips between the two steps of a strip, a ring of 10 slots (40 MiB): measured against 3 / 6 and 8 / 14
+    // (profiles/r02c_fuse4v2_tma_sweep.log); the tiles of about 7 strips are in flight at any time.
+    const int lag_d = 6, ring_d = 10;
     F4v2Params p;
     memset(&p, 0, sizeof(p));
     p.nstrips = (uint32_t)S;
     p.spo = (uint32_t)spo;
-    p.lag = (uint32_t)std::min<uint64_t>((uint64_t)std::max(lag_env, 1), S);
-    p.ring = (uint32_t)std::max<int64_t>(ring_env, (int64_t)p.lag + 1);
+    p.ngroups = (uint32_t)ngroups;
+    p.gpo = (uint32_t)gpo;
+    p.glog = (uint32_t)glog;
+    p.lag = (uint32_t)std::min<uint64_t>((uint64_t)lag_d, ngroups);
+    p.ring = (uint32_t)std::max<int64_t>(ring_d, (int64_t)p.lag + 1);
     p.total_items = (uint32_t)(2 * S * 128);
-    p.d_spo = make_fastdiv((uint32_t)spo);
-    p.d_ring = make_fastdiv(p.ring);
+    p.d_gpo = make_fastdiv((uint32_t)gpo);
+    p.d_ring = make_fastdiv(p.ring << glog);
     p.backward = job.backward ? 1 : 0;
     p.fct = (float)job.fct;
     p.stw = (const float2 *)get_table(TAB_STOCKHAM, 0, 128, 0);
@@ -138,11 +147,14 @@ bool launch_fourstep_fused2_f32(const LineJob &job, const std::vector<Dim> &dims
     p.twA = (const float2 *)get_table(TAB_SPLIT_A, 0, job.n, tS);
     p.twB = (const float2 *)get_table(TAB_SPLIT_B, 0, job.n, tS);
     p.max_idle = 1u << 22;
-    static const int pf_env = env_i("RFB200_FUSE4_PF", 2);
-    p.pf_strips = (uint32_t)std::max(pf_env, 0);
+    static const int dbg_copy = env_i("RFB200_FUSE4_DEBUG_COPY", 0);  // measurement aid (wrong results): no transforms
+    static const int dbg_only = env_i("RFB200_FUSE4_DEBUG_ONLY", 0);  // measurement aid (wrong results): 1 = A tiles only, 2 = B tiles only
+    p.dbg_only = (uint32_t)dbg_only;
+    if (dbg_only) p.total_items = (uint32_t)(S * 128);
     p.host_err = async_error_word();
     const size_t slot_bytes = (size_t)128 * f4v2::TILE_BYTES;
-    const size_t ring_bytes = (size_t)p.ring * slot_bytes, ctr_bytes = (2 * S + 2) * sizeof(uint32_t);
+    const size_t ring_slots = (size_t)p.ring << glog;
+    const size_t ring_bytes = ring_slots * slot_bytes, ctr_bytes = (2 * S + 2) * sizeof(uint32_t);
     Scratch sc(ring_bytes + ctr_bytes, s);
     p.ring_mem = (char *)sc.p;
     p.ctr = (uint32_t *)(p.ring_mem + ring_bytes);
@@ -185,11 +197,14 @@ bool launch_fourstep_fused2_f32(const LineJob &job, const std::vector<Dim> &dims
         }
     }
     // ring: [32 lines][j0: 256 B][k1: 32 KiB][slot: 4 MiB]; A stores the box (all lines, one j0, all k1) of its slot
-    if (!make_map(&maps.m[4], p.ring_mem, 32, 128, 128, p.ring, 256, f4v2::TILE_BYTES, slot_bytes, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+    if (!make_map(&maps.m[4], p.ring_mem, 32, 128, 128, ring_slots, 256, f4v2::TILE_BYTES, slot_bytes, CU_TENSOR_MAP_L2_PROMOTION_NONE))
         return false;
     RFB_CUDA_CHECK(cudaMemsetAsync(p.ctr, 0, ctr_bytes, s));
-    static const int stages = env_i("RFB200_FUSE4_STAGES", 2);
-    return stages >= 3 ? launch_f4v2<3>(p, maps, s) : launch_f4v2<2>(p, maps, s);
+    // 2 stages x 3 CTAs per SM with every tile staged and stored by the copy engine.  Measured alternatives
+    // (profiles/r02*_fuse4v2_*.log): 3 stages x 2 CTAs 0.70 ms, B tiles stored from registers 0.654 ms, A tiles stored from
+    // registers + barrier/fence publication 0.654-0.86 ms, against 0.645 ms.
+    if (dbg_copy) return launch_f4v2<2, true, false, true>(p, maps, s);
+    return launch_f4v2<2, true, false, false>(p, maps, s);
 }
 
 }  // namespace rfb

@@ -62,6 +62,8 @@ inline uint64_t fill_geom(TileGeom<T> &g, const LineJob &job, const std::vector<
     g.post_tab = (const cx<T> *)job.post_tab;
     g.pre_bound = (uint32_t)job.pre_bound;
     g.post_bound = (uint32_t)job.post_bound;
+    g.aux_ld = (const cx<T> *)job.aux_ld;
+    g.aux_st = (const cx<T> *)job.aux_st;
     g.pre_swap = job.pre_swap ? 1 : 0;
     g.post_swap = job.post_swap ? 1 : 0;
     if (!job.split_out.empty()) {
@@ -114,10 +116,7 @@ inline void set_prefetch_rows(TileGeom<T> &g, const LineJob &job, const std::vec
     // rows further apart than 64 KiB each sit on their own page: the prefetches then cost more (TLB) than they
     // save (measured: 1024^3 c64 axis 1, rows 8 KiB apart: 58 % -> 68 %; axis 0, rows 8 MiB apart: 57 % -> 47 %)
     const int64_t sa = job.is < 0 ? -job.is : job.is;
-    static const int64_t max_stride = [] {
-        const char *v = getenv("RFB200_PF_LF_MAXSTRIDE");
-        return v ? (int64_t)atoll(v) : (int64_t)65536;
-    }();
+    const int64_t max_stride = 65536;
     if (pf <= 0 || dims.empty() || dims[0].is != item || n_items > 65536 || sa > max_stride) return;
     // zero-padded load (Bluestein): rows whose first element is already past the bound are never read
     if (job.pre_tab && job.g_mul) n_items = std::min<uint64_t>(n_items, (job.pre_bound + job.g_mul - 1) / job.g_mul);
@@ -147,9 +146,6 @@ inline void set_prefetch_by_mode(TileGeom<T> &g, const LineJob &job, const std::
 // pow2_launch_*.cu: returns false when the job is not one the register kernel takes
 bool launch_pow2_f32(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s);
 bool launch_pow2_f64(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s);
-// pow2_launch_f32.cu: fused four-step (both steps in one persistent kernel, intermediate in L2); false if not taken
-bool launch_fourstep_fused_f32(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB,
-                               const Fuse4Ctl &c, cudaStream_t s);
 // fused4v2_launch.cu: both four-step passes of 16384-point strided complex64 lines in one warp-specialised persistent kernel
 bool launch_fourstep_fused2_f32(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 // jit.cu: run-time specialised kernel for smooth non-power-of-two lengths (NVRTC); false if not taken

@@ -623,14 +623,14 @@ __device__ __forceinline__ double2 cis_mpi(double num, double den) {
 }
 
 template <typename T>
-__global__ void dcst_pre_kernel(LinesIdx bi, uint32_t nlines, const char *in, int64_t sa, cx<T> *z, DcstParams p) {
+__global__ void dcst_pre_kernel(LinesIdx bi, uint32_t l0, uint32_t nlines, const char *in, int64_t sa, cx<T> *z, DcstParams p) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.Lf) return;
     const uint32_t N = p.N;
     const double SQ2 = 1.4142135623730951;
-    for (uint32_t l = blockIdx.y; l < nlines; l += gridDim.y) {
+    for (uint32_t l = blockIdx.y; l < nlines; l += gridDim.y) {  // lines l0 .. l0 + nlines of the array, slab rows 0 .. nlines
         int64_t oi, oo;
-        lines_off(bi, l, oi, oo);
+        lines_off(bi, l0 + l, oi, oo);
         auto x = [&](uint32_t i) { return (double)*reinterpret_cast<const T *>(in + oi + (int64_t)i * sa); };
         double re = 0.0, im = 0.0;
         if (p.type == 1) {
@@ -672,14 +672,14 @@ __global__ void dcst_pre_kernel(LinesIdx bi, uint32_t nlines, const char *in, in
 }
 
 template <typename T>
-__global__ void dcst_post_kernel(LinesIdx bi, uint32_t nlines, const cx<T> *z, char *out, int64_t sa, DcstParams p) {
+__global__ void dcst_post_kernel(LinesIdx bi, uint32_t l0, uint32_t nlines, const cx<T> *z, char *out, int64_t sa, DcstParams p) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t N = p.N;
     if (k >= N) return;
     const double RSQ2 = 0.70710678118654752;
     for (uint32_t l = blockIdx.y; l < nlines; l += gridDim.y) {
         int64_t oi, oo;
-        lines_off(bi, l, oi, oo);
+        lines_off(bi, l0 + l, oi, oo);
         const cx<T> *zl = z + (size_t)l * p.Lf;
         double y;
         if (p.type == 1) {
@@ -709,7 +709,9 @@ __global__ void dcst_post_kernel(LinesIdx bi, uint32_t nlines, const cx<T> *z, c
     }
 }
 
-void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s) {
+void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s, int quirk_mode) {
+    // quirk_mode: -1 = the process-wide setting (rfb200_set_dst_ortho_quirk), 0 = SciPy's scaling, 1 = the reference's
+    const bool dst_quirk = quirk_mode < 0 ? g_dst_quirk : quirk_mode != 0;
     if (any_zero(a.shape)) return;
     if (type < 1 || type > 4) { set_error("invalid DCT/DST type"); throw Error(); }
     const int64_t esz = a.prec ? 16 : 8;
@@ -722,7 +724,7 @@ void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s)
         p.type = type;
         p.cosine = cosine ? 1 : 0;
         p.ortho = ortho ? 1 : 0;
-        p.quirk = g_dst_quirk ? 1 : 0;
+        p.quirk = dst_quirk ? 1 : 0;
         if (type == 1) {
             if (cosine && N < 2) { set_error("DCT-I needs at least two points (zero-length FFT requested)"); throw Error(); }
             p.Lf = (uint32_t)(cosine ? 2 * (N - 1) : 2 * (N + 1));
@@ -742,9 +744,54 @@ void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s)
             fj.fct = first ? a.fct : 1.0;
             fj.load_mode = type == 2 ? LD_DCT2 : LD_DCT3;
             fj.store_mode = type == 2 ? ST_DCT2 : ST_DCT3;
-            fj.flags = (cosine ? 0 : FLAG_SINE) | (ortho ? FLAG_ORTHO : 0) | (g_dst_quirk ? FLAG_QUIRK : 0);
+            fj.flags = (cosine ? 0 : FLAG_SINE) | (ortho ? FLAG_ORTHO : 0) | (dst_quirk ? FLAG_QUIRK : 0);
             if (run_lines_pow2(fj, s)) { first = false; continue; }
         }
+        {
+            // Any other type / length: the type's reordering, extension and phase factors are the load and store stage of ONE
+            // complex transform in the shared-memory tile kernel (line_io.cuh LD_G_* / ST_G_*) -- one launch per axis, no
+            // work area.  Transform length: 2(N-1) / 2(N+1) (type I), N (types II, III), N/2 (type IV, N even) or 2N (odd N).
+            LineJob gj;
+            gj.prec = a.prec;
+            gj.in = first ? a.in : a.out;
+            gj.out = a.out;
+            gj.is = si[ax];
+            gj.os = a.sout[ax];
+            gj.batch = b;
+            gj.fct = first ? a.fct : 1.0;
+            gj.flags = (cosine ? 0 : FLAG_SINE) | (ortho ? FLAG_ORTHO : 0) | (dst_quirk ? FLAG_QUIRK : 0);
+            bool have = true;
+            if (type == 1) {
+                gj.n = cosine ? 2 * (N - 1) : 2 * (N + 1);
+                gj.load_mode = cosine ? LD_G_DCT1 : LD_G_DST1;
+                gj.store_mode = cosine ? ST_G_DCT1 : ST_G_DST1;
+                gj.flags &= ~FLAG_SINE;
+            } else if (type == 2) {
+                gj.n = N;
+                gj.load_mode = LD_G_DCT2;
+                gj.store_mode = ST_G_DCT2;
+                gj.aux_st = get_table(TAB_QUARTER, a.prec, N, 0);
+            } else if (type == 3) {
+                gj.n = N;
+                gj.load_mode = LD_G_DCT3;
+                gj.store_mode = ST_G_DCT3;
+                gj.backward = true;
+                gj.aux_ld = get_table(TAB_QUARTER, a.prec, N, 0);
+            } else if (N % 2 == 0) {
+                gj.n = N / 2;
+                gj.load_mode = LD_G_DCT4;
+                gj.store_mode = ST_G_DCT4;
+                gj.aux_ld = gj.aux_st = get_table(TAB_QUARTER, a.prec, 2 * N, 0);
+            } else {
+                gj.n = 2 * N;
+                gj.load_mode = LD_G_DCT4Z;
+                gj.store_mode = ST_G_DCT4Z;
+                gj.aux_ld = get_table(TAB_QUARTER, a.prec, N, 0);
+                gj.aux_st = get_table(TAB_QUARTER, a.prec, 2 * N, 0);
+            }
+            if (have && gj.n >= 1 && run_lines_tile(gj, s)) { first = false; continue; }
+        }
+        // ---- lines too long for a shared-memory tile: embedding in a work area, three launches, in slabs of lines ----------
         LinesIdx bi;
         memset(&bi, 0, sizeof(bi));
         uint64_t nlines = 1;
@@ -763,29 +810,33 @@ void op_dcst(const NdArgs &a, int type, bool ortho, bool cosine, cudaStream_t s)
             bi.nd = k;
         }
         if (nlines >= (1ull << 31)) { set_error("too many lines"); throw Error(); }
-        // bounded work area: process the lines in slabs of <= ~1 GiB of scratch
+        // bounded work area: the lines go through in slabs of <= 1 GiB of scratch
         const uint64_t per_line = (uint64_t)p.Lf * (uint64_t)esz;
-        Scratch sc(nlines * per_line, s);
+        const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(nlines, (1ull << 30) / per_line));
+        Scratch sc(slab * per_line, s);
         const char *src = first ? a.in : a.out;
-        dim3 grid((unsigned)((p.Lf + 255) / 256), (unsigned)std::min<uint64_t>(nlines, 32768));
-        if (a.prec) dcst_pre_kernel<double><<<grid, 256, 0, s>>>(bi, (uint32_t)nlines, src, si[ax], (double2 *)sc.p, p);
-        else dcst_pre_kernel<float><<<grid, 256, 0, s>>>(bi, (uint32_t)nlines, src, si[ax], (float2 *)sc.p, p);
-        count_launch();
-        RFB_AFTER_LAUNCH2();
-        LineJob j;
-        j.prec = a.prec;
-        j.n = p.Lf;
-        j.is = j.os = esz;
-        j.batch.push_back(Dim{(int64_t)nlines, (int64_t)per_line, (int64_t)per_line, false});
-        j.in = (const char *)sc.p;
-        j.out = (char *)sc.p;
-        j.fct = first ? a.fct : 1.0;
-        run_lines(j, s);
-        dim3 grid2((unsigned)((N + 255) / 256), (unsigned)std::min<uint64_t>(nlines, 32768));
-        if (a.prec) dcst_post_kernel<double><<<grid2, 256, 0, s>>>(bi, (uint32_t)nlines, (const double2 *)sc.p, a.out, a.sout[ax], p);
-        else dcst_post_kernel<float><<<grid2, 256, 0, s>>>(bi, (uint32_t)nlines, (const float2 *)sc.p, a.out, a.sout[ax], p);
-        count_launch();
-        RFB_AFTER_LAUNCH2();
+        for (uint64_t l0 = 0; l0 < nlines; l0 += slab) {
+            const uint64_t cnt = std::min<uint64_t>(slab, nlines - l0);
+            dim3 grid((unsigned)((p.Lf + 255) / 256), (unsigned)std::min<uint64_t>(cnt, 32768));
+            if (a.prec) dcst_pre_kernel<double><<<grid, 256, 0, s>>>(bi, (uint32_t)l0, (uint32_t)cnt, src, si[ax], (double2 *)sc.p, p);
+            else dcst_pre_kernel<float><<<grid, 256, 0, s>>>(bi, (uint32_t)l0, (uint32_t)cnt, src, si[ax], (float2 *)sc.p, p);
+            count_launch("dcst_pre_kernel");
+            RFB_AFTER_LAUNCH2();
+            LineJob j;
+            j.prec = a.prec;
+            j.n = p.Lf;
+            j.is = j.os = esz;
+            j.batch.push_back(Dim{(int64_t)cnt, (int64_t)per_line, (int64_t)per_line, false});
+            j.in = (const char *)sc.p;
+            j.out = (char *)sc.p;
+            j.fct = first ? a.fct : 1.0;
+            run_lines(j, s);
+            dim3 grid2((unsigned)((N + 255) / 256), (unsigned)std::min<uint64_t>(cnt, 32768));
+            if (a.prec) dcst_post_kernel<double><<<grid2, 256, 0, s>>>(bi, (uint32_t)l0, (uint32_t)cnt, (const double2 *)sc.p, a.out, a.sout[ax], p);
+            else dcst_post_kernel<float><<<grid2, 256, 0, s>>>(bi, (uint32_t)l0, (uint32_t)cnt, (const float2 *)sc.p, a.out, a.sout[ax], p);
+            count_launch("dcst_post_kernel");
+            RFB_AFTER_LAUNCH2();
+        }
         first = false;
     }
 }

@@ -2,6 +2,9 @@
 
 #include <math.h>
 
+#include <stdlib.h>
+
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -177,15 +180,53 @@ uint32_t split_size(uint64_t n) {
 // device table cache
 // ---------------------------------------------------------------------------------------
 namespace {
-struct Key {
-    int dev, kind, prec;
-    uint64_t n, param;
-    bool operator<(const Key &o) const {
-        return std::tie(dev, kind, prec, n, param) < std::tie(o.dev, o.kind, o.prec, o.n, o.param);
+using Key = TableKey;
+struct KeyLess {
+    bool operator()(const Key &a, const Key &o) const {
+        return std::tie(a.dev, a.kind, a.prec, a.n, a.param) < std::tie(o.dev, o.kind, o.prec, o.n, o.param);
     }
 };
+// An entry is BUILDING while one thread computes and uploads it (outside the cache mutex; other threads asking for the same
+// table wait on the condition variable), then READY.  `leases` counts the TableScope's (one per library call in flight on
+// the host) that have fetched it: such an entry is never evicted, so a pointer handed to a call stays valid until that
+// call has enqueued its kernels; a table evicted later is released with cudaFree, which waits for the device to finish the
+// kernels that may still read it.
+struct Entry {
+    void *d = nullptr;
+    size_t bytes = 0;
+    uint64_t last_use = 0;
+    int leases = 0;
+    bool ready = false;
+};
 std::mutex g_mu;
-std::map<Key, void *> g_tables;
+std::condition_variable g_cv;
+std::map<Key, Entry, KeyLess> g_tables;
+uint64_t g_clock = 0;
+size_t g_bytes = 0;
+thread_local std::vector<Key> *g_scope = nullptr;  // tables leased by the library call running on this thread
+
+size_t cache_max_entries() {
+    static const size_t v = [] { const char *e = getenv("RFB200_PLAN_CACHE_ENTRIES"); return e ? (size_t)atoll(e) : (size_t)256; }();
+    return v;
+}
+size_t cache_max_bytes() {
+    static const size_t v = [] { const char *e = getenv("RFB200_PLAN_CACHE_MB"); return (e ? (size_t)atoll(e) : (size_t)1024) << 20; }();
+    return v;
+}
+
+// g_mu held.  Least recently used first; entries in use (leased or being built) stay.
+void evict_locked(std::vector<void *> &to_free) {
+    while (g_tables.size() > cache_max_entries() || g_bytes > cache_max_bytes()) {
+        auto victim = g_tables.end();
+        for (auto it = g_tables.begin(); it != g_tables.end(); ++it)
+            if (it->second.ready && it->second.leases == 0 && (victim == g_tables.end() || it->second.last_use < victim->second.last_use))
+                victim = it;
+        if (victim == g_tables.end()) break;
+        to_free.push_back(victim->second.d);
+        g_bytes -= victim->second.bytes;
+        g_tables.erase(victim);
+    }
+}
 
 template <typename T>
 void fill(std::vector<T> &h, TableKind kind, uint64_t n, uint64_t param, size_t count) {
@@ -242,70 +283,152 @@ void fill_stockham(std::vector<T> &h, uint64_t n, int which, uint64_t param) {
 }
 }  // namespace
 
+TableScope::TableScope() : prev_(g_scope) { g_scope = &keys_; }
+TableScope::~TableScope() {
+    g_scope = prev_;
+    if (keys_.empty()) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &k : keys_) {
+        auto it = g_tables.find(k);
+        if (it != g_tables.end() && it->second.leases > 0) --it->second.leases;
+    }
+}
+
 const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool *created, void **writable) {
     int dev = 0;
     RFB_CUDA_CHECK(cudaGetDevice(&dev));
     Key key{dev, (int)kind, prec, n, param};
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_tables.find(key);
     if (created) *created = false;
-    if (it != g_tables.end()) {
-        if (writable) *writable = it->second;
-        return it->second;
+    {
+        std::unique_lock<std::mutex> lk(g_mu);
+        for (;;) {
+            auto it = g_tables.find(key);
+            if (it == g_tables.end()) break;
+            if (!it->second.ready) { g_cv.wait(lk); continue; }  // another thread is building it
+            it->second.last_use = ++g_clock;
+            if (g_scope) { ++it->second.leases; g_scope->push_back(key); }
+            if (writable) *writable = it->second.d;
+            return it->second.d;
+        }
+        g_tables[key] = Entry();  // BUILDING: claimed by this thread
     }
-    size_t count = 0;
-    switch (kind) {
-        case TAB_LINE: count = n; break;
-        case TAB_SPLIT_A: count = (n + param - 1) / param + 1; break;
-        case TAB_SPLIT_B: count = param; break;
-        case TAB_CHIRP: count = n; break;
-        case TAB_CHIRP_FFT:
-        case TAB_CHIRP_FFT_T: count = param; break;
-        case TAB_QUARTER: count = n + 1; break;
-        case TAB_STOCKHAM:
-        case TAB_REGMIX:
-        case TAB_TILE: count = n; break;  // upper bound: sum (R-1)*ido < n
-    }
-    size_t esz = prec ? 16 : 8;
+    // ---- build and upload outside the mutex ------------------------------------------------------------------------
     void *d = nullptr;
-    RFB_CUDA_CHECK(cudaMalloc(&d, count * esz > 0 ? count * esz : esz));
-    if (kind == TAB_STOCKHAM || kind == TAB_TILE || kind == TAB_REGMIX) {
-        if (prec) {
-            std::vector<double> h;
-            fill_stockham(h, n, kind == TAB_TILE ? 1 : (kind == TAB_REGMIX ? 2 : 0), param);
-            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
-        } else {
-            std::vector<float> h;
-            fill_stockham(h, n, kind == TAB_TILE ? 1 : (kind == TAB_REGMIX ? 2 : 0), param);
-            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    size_t bytes = 0;
+    try {
+        size_t count = 0;
+        switch (kind) {
+            case TAB_LINE: count = n; break;
+            case TAB_SPLIT_A: count = (n + param - 1) / param + 1; break;
+            case TAB_SPLIT_B: count = param; break;
+            case TAB_CHIRP: count = n; break;
+            case TAB_CHIRP_FFT:
+            case TAB_CHIRP_FFT_T: count = param; break;
+            case TAB_QUARTER: count = n + 1; break;
+            case TAB_STOCKHAM:
+            case TAB_REGMIX:
+            case TAB_TILE: count = n; break;  // upper bound: sum (R-1)*ido < n
         }
-    } else if (kind != TAB_CHIRP_FFT && kind != TAB_CHIRP_FFT_T) {
-        if (prec) {
-            std::vector<double> h;
-            fill(h, kind, n, param, count);
-            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), count * esz, cudaMemcpyHostToDevice));
-        } else {
-            std::vector<float> h;
-            fill(h, kind, n, param, count);
-            RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), count * esz, cudaMemcpyHostToDevice));
+        const size_t esz = prec ? 16 : 8;
+        bytes = count * esz > 0 ? count * esz : esz;
+        RFB_CUDA_CHECK(cudaMalloc(&d, bytes));
+        if (kind == TAB_STOCKHAM || kind == TAB_TILE || kind == TAB_REGMIX) {
+            if (prec) {
+                std::vector<double> h;
+                fill_stockham(h, n, kind == TAB_TILE ? 1 : (kind == TAB_REGMIX ? 2 : 0), param);
+                RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+            } else {
+                std::vector<float> h;
+                fill_stockham(h, n, kind == TAB_TILE ? 1 : (kind == TAB_REGMIX ? 2 : 0), param);
+                RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
+        } else if (kind != TAB_CHIRP_FFT && kind != TAB_CHIRP_FFT_T) {
+            if (prec) {
+                std::vector<double> h;
+                fill(h, kind, n, param, count);
+                RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), count * esz, cudaMemcpyHostToDevice));
+            } else {
+                std::vector<float> h;
+                fill(h, kind, n, param, count);
+                RFB_CUDA_CHECK(cudaMemcpy(d, h.data(), count * esz, cudaMemcpyHostToDevice));
+            }
         }
+    } catch (...) {
+        if (d) cudaFree(d);
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            g_tables.erase(key);
+        }
+        g_cv.notify_all();
+        throw;
     }
-    g_tables[key] = d;
+    std::vector<void *> to_free;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Entry &e = g_tables[key];
+        e.d = d;
+        e.bytes = bytes;
+        e.ready = true;
+        e.last_use = ++g_clock;
+        if (g_scope) { ++e.leases; g_scope->push_back(key); }
+        else e.leases = 0;
+        g_bytes += bytes;
+        const bool keep = !g_scope;  // no scope: protect the new entry from its own eviction pass
+        if (keep) ++e.leases;
+        evict_locked(to_free);
+        if (keep) --g_tables[key].leases;
+    }
+    g_cv.notify_all();
+    for (void *q : to_free) cudaFree(q);  // implicit device synchronisation: no kernel is still reading it afterwards
     if (created) *created = true;
     if (writable) *writable = d;
     return d;
 }
 
-void plan_cache_clear() {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int cur = 0;
-    cudaGetDevice(&cur);
-    for (auto it = g_tables.begin(); it != g_tables.end();) {
-        if (it->first.dev == cur) {
-            cudaFree(it->second);
-            it = g_tables.erase(it);
-        } else ++it;
+// A table whose contents the engine fills itself (TAB_CHIRP_FFT*) and whose fill failed: forget it.
+void discard_table(TableKind kind, int prec, uint64_t n, uint64_t param) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    Key key{dev, (int)kind, prec, n, param};
+    void *d = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_tables.find(key);
+        if (it == g_tables.end() || !it->second.ready) return;
+        d = it->second.d;
+        g_bytes -= it->second.bytes;
+        g_tables.erase(it);
     }
+    if (d) cudaFree(d);
+}
+
+void plan_cache_clear() {
+    std::vector<void *> to_free;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto it = g_tables.begin(); it != g_tables.end();) {
+            if (it->first.dev == cur && it->second.ready && it->second.leases == 0) {
+                to_free.push_back(it->second.d);
+                g_bytes -= it->second.bytes;
+                it = g_tables.erase(it);
+            } else ++it;
+        }
+    }
+    for (void *q : to_free) cudaFree(q);
+}
+
+void plan_cache_stats(uint64_t *entries, uint64_t *bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (entries) *entries = g_tables.size();
+    if (bytes) *bytes = g_bytes;
+}
+
+// Drops the host-side records without touching the device (the forked child of a process that used CUDA must not).
+void plan_cache_forget() {
+    g_tables.clear();
+    g_bytes = 0;
 }
 
 }  // namespace rfb

@@ -46,6 +46,29 @@ enum TableKind : int {
 const void *get_table(TableKind kind, int prec, uint64_t n, uint64_t param, bool *created = nullptr,
                       void **writable = nullptr);
 void plan_cache_clear();
+// The cache is bounded (RFB200_PLAN_CACHE_ENTRIES, default 256 tables; RFB200_PLAN_CACHE_MB, default 1024): least recently
+// used tables are released once a bound is exceeded (the reference keeps 16 plans, _pocketfft_hdronly.h:3169-3223).
+void plan_cache_stats(uint64_t *entries, uint64_t *bytes);
+void plan_cache_forget();
+void discard_table(TableKind kind, int prec, uint64_t n, uint64_t param);
+// One per library call (constructed at the ABI entry points): the tables fetched by the call on this thread are leased
+// until the scope ends, i.e. they cannot be evicted between get_table and the kernel launches that use them.
+struct TableKey {
+    int dev, kind, prec;
+    uint64_t n, param;
+};
+class TableScope {
+  public:
+    TableScope();
+    ~TableScope();
+    TableScope(const TableScope &) = delete;
+    TableScope &operator=(const TableScope &) = delete;
+
+    std::vector<TableKey> keys_;
+
+  private:
+    std::vector<TableKey> *prev_;
+};
 
 uint32_t split_size(uint64_t n);  // S used by the SPLIT tables: ceil(sqrt(n)) rounded up to a power of two
 

@@ -7,9 +7,7 @@
 #include "geom_fill.cuh"
 #include "pow2_kernel.cuh"
 #include "pow2_dual_kernel.cuh"
-#include "pow2_fused4_kernel.cuh"
 #include "pow2_pair_kernel.cuh"
-#include "pow2_async_kernel.cuh"
 
 namespace rfb {
 
@@ -106,7 +104,7 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
         // short lines: dense tiles go through shared memory for coalescing (pow2_kernel.cuh).  Measured on B200, % of the
         // HBM copy peak without -> with staging: c64 n=16 28 -> 88, n=32 46 -> 66, n=64 67 -> 64; c128 n=16 53 -> 75,
         // n=32 63 -> 56, n=64 80 -> 57: only the first three are switched on.
-        static const bool stage = [] { const char *v = getenv("RFB200_NO_STAGE"); return !(v && atoi(v)); }();
+        const bool stage = true;
         const int64_t e = (int64_t)sizeof(cx<T>), line = (int64_t)job.n * e;
         const bool plain_in = job.load_mode == LD_C2C && (job.n_in == 0 || job.n_in == job.n) && !job.pre_tab;
         const bool plain_out = job.store_mode == ST_C2C && job.twN == 0 && !job.post_tab && job.split_out.empty();
@@ -149,18 +147,15 @@ void launch_pow2_inst(const LineJob &job, const std::vector<Dim> &dims, bool loa
 
 template <int LOGN, int W>
 bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
-template <int LOGN, int W>
-bool launch_async_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 
-// Strided float32 lines with adjacent neighbours (line-fast tiles).  RFB200_LFMODE: 0 = one line per thread
-// (pow2_kernel.cuh), 1 = two lines per thread (pow2_pair_kernel.cuh; default), 2 = persistent CTAs with the next tile
-// in flight through cp.async (pow2_async_kernel.cuh; 128- and 256-point lines).  RFB200_PAIR=0 is an alias of mode 0.
+// Strided float32 lines with adjacent neighbours (line-fast tiles) keep two lines per thread (pow2_pair_kernel.cuh).
+// RFB200_PAIR=0 falls back to one line per thread (pow2_kernel.cuh).  (Round 1 also tried persistent CTAs staging the
+// next tile with 8-byte cp.async -- slower, LDGSTS saturates the MIO path, profiles/r01e_* -- and 5 / 6 resident CTAs per
+// SM -- slower, profiles/r02a_sweep_lf_ctas.log; both were removed.)
 inline int lf_mode() {
     static const int v = [] {
         const char *p = getenv("RFB200_PAIR");
-        if (p && atoi(p) == 0) return 0;
-        const char *e = getenv("RFB200_LFMODE");
-        return e ? atoi(e) : 1;
+        return (p && atoi(p) == 0) ? 0 : 1;
     }();
     return v;
 }
@@ -213,20 +208,16 @@ bool launch_pow2_logn(const LineJob &job, const std::vector<Dim> &dims, bool loa
     }
     if (!lf) {
         if constexpr (sizeof(T) == 4 && (LOGN == 13 || LOGN == 14)) {
-            // long contiguous complex lines: two interleaved half-length transforms per thread (RFB200_DUAL_C2C=0: off).
+            // long contiguous complex lines: two interleaved half-length transforms per thread.
             // Measured on B200, % of the HBM copy peak without -> with: n = 8192 62.1 -> 82.0 (cuFFT 75.2),
             // n = 16384 51.9 -> 56.3 (cuFFT 55.1)   (profiles/r01h_ab_dual_c2c.log)
-            static const int dc = [] { const char *v = getenv("RFB200_DUAL_C2C"); return v ? atoi(v) : 1; }();
-            if (dc && dual_variant() != 0 && launch_dual_inst<LOGN - 1, 0, true>(job, dims, s)) return true;
+            if (dual_variant() != 0 && launch_dual_inst<LOGN - 1, 0, true>(job, dims, s)) return true;
         }
         launch_pow2_inst<T, LOGN, WE, 0>(job, dims, load_lf, store_lf, s);
         return true;
     }
     if constexpr (WL == 0) return false;
     else {
-        if constexpr (sizeof(T) == 4 && (LOGN == 7 || LOGN == 8)) {
-            if (lf_mode() == 2 && load_lf && store_lf && launch_async_inst<LOGN, WL>(job, dims, s)) return true;
-        }
         if constexpr (sizeof(T) == 4 && LOGN >= 7 && LOGN <= 10 && WL >= 2) {
             if (lf_mode() >= 1 && load_lf && store_lf && launch_pair_inst<LOGN, WL>(job, dims, s)) return true;
         }
@@ -245,14 +236,7 @@ bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
     set_prefetch_by_mode<float>(g, job, dims, (uint32_t)W);
     const float2 *stw = (const float2 *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
     const size_t smem = (size_t)Body::WP * Body::PITCH * sizeof(float4);
-    // RFB200_LF_CTAS = 5 / 6: the 128-point instantiation compiled for more resident CTAs per SM (not yet measured;
-    // default: 4, the measured configuration)
-    static const int ctas = [] { const char *v = getenv("RFB200_LF_CTAS"); return v ? atoi(v) : 4; }();
     void (*kern)(const TileGeom<float>, const float2 *) = fft_pow2_pair_kernel<LOGN, W>;
-    if constexpr (LOGN == 7) {
-        if (ctas == 5) kern = fft_pow2_pair_kernel_occ<LOGN, W, 5>;
-        else if (ctas >= 6) kern = fft_pow2_pair_kernel_occ<LOGN, W, 6>;
-    }
     static thread_local int dev_set = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -268,80 +252,6 @@ bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
     }
     RFB_CUDA_CHECK(cudaGetLastError());
     return true;
-}
-
-// The same jobs on persistent CTAs that stage the next tile with cp.async (pow2_async_kernel.cuh).
-template <int LOGN, int W>
-bool launch_async_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
-    using Body = AsyncLfBody<LOGN, W>;
-    if (!lf_plain_job(job, dims)) return false;
-    TileGeom<float> g;
-    const uint64_t ntiles = fill_geom<float>(g, job, dims, (uint32_t)W, true, true);
-    const float2 *stw = (const float2 *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
-    const size_t smem = 2 * (size_t)Body::BUF * sizeof(float2);
-    auto kern = fft_pow2_async_kernel<LOGN, W>;
-    static thread_local int dev_set = -1;
-    static thread_local int sms = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev_set != dev) {
-        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RFB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        dev_set = dev;
-    }
-    static const int per_sm = [] { const char *v = getenv("RFB200_ASYNC_CTAS"); return v ? atoi(v) : 3; }();
-    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * (uint64_t)std::max(per_sm, 1));
-    kern<<<grid, Body::NT, smem, s>>>(g, stw, (uint32_t)ntiles);
-    count_launch("fft_pow2_async_kernel");
-    RFB_CUDA_CHECK(cudaGetLastError());
-    return true;
-}
-
-// Both steps of a four-step transform of strided lines in one persistent kernel (pow2_fused4_kernel.cuh).
-// A, B: the two line jobs for ONE strip (strip 0 of outer item 0), already normalised; c: everything except the
-// geometry.  false (nothing launched) when there is no instantiation for this length.
-template <typename T, int LOGN>
-bool launch_fused4_logn(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB, Fuse4Ctl c,
-                        cudaStream_t s) {
-    constexpr int W = p2_wl(LOGN, sizeof(T) == 8);
-    using Body = Pow2Body<T, LOGN, W, 0>;
-    TileGeom<T> gA, gB;
-    const uint64_t tA = fill_geom<T>(gA, A, dA, (uint32_t)W, true, true);
-    const uint64_t tB = fill_geom<T>(gB, B, dB, (uint32_t)W, true, true);
-    if (tA != tB || tA != c.tiles) return false;
-    c.d_tiles = make_fastdiv(c.tiles);
-    c.d_ring = make_fastdiv(c.ring);
-    const cx<T> *stw = (const cx<T> *)get_table(TAB_STOCKHAM, A.prec, 1ull << LOGN, 0);
-    const size_t smem = (size_t)W * Body::PITCH * sizeof(cx<T>);
-    // RFB200_LF_CTAS = 5 / 6: compiled for more resident CTAs per SM (unmeasured so far; default: the register kernel's 4)
-    static const int ctas = [] { const char *v = getenv("RFB200_LF_CTAS"); return v ? atoi(v) : 0; }();
-    void (*kern)(const TileGeom<T>, const TileGeom<T>, const cx<T> *, const Fuse4Ctl) = fft_fourstep_fused_kernel<T, LOGN, W>;
-    int per_sm = p2_min_blocks<T, Body::NT>();
-    if (ctas == 5) { kern = fft_fourstep_fused_kernel<T, LOGN, W, 5>; per_sm = 5; }
-    else if (ctas >= 6) { kern = fft_fourstep_fused_kernel<T, LOGN, W, 6>; per_sm = 6; }
-    static thread_local int dev_set = -1;
-    static thread_local int sms = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev_set != dev) {
-        RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RFB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        dev_set = dev;
-    }
-    const uint64_t items = 2ull * c.nstrips * c.tiles;
-    const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)sms * (uint64_t)per_sm);
-    kern<<<grid, Body::NT, smem, s>>>(gA, gB, stw, c);
-    count_launch("fft_fourstep_fused_kernel<float,7,32>");
-    RFB_CUDA_CHECK(cudaGetLastError());
-    return true;
-}
-
-template <typename T>
-bool launch_fused4_any(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB, const Fuse4Ctl &c,
-                       cudaStream_t s) {
-    if (A.n != B.n || dA.size() > (size_t)MAXB || dB.size() > (size_t)MAXB) return false;
-    if (sizeof(T) == 4 && A.n == 128) return launch_fused4_logn<T, 7>(A, dA, B, dB, c, s);
-    return false;
 }
 
 template <typename T, int MAXLOG>

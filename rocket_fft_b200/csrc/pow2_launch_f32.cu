@@ -3,8 +3,4 @@ namespace rfb {
 bool launch_pow2_f32(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s) {
     return launch_pow2_any<float, 14>(job, dims, load_lf, store_lf, s);
 }
-bool launch_fourstep_fused_f32(const LineJob &A, const std::vector<Dim> &dA, const LineJob &B, const std::vector<Dim> &dB,
-                               const Fuse4Ctl &c, cudaStream_t s) {
-    return launch_fused4_any<float>(A, dA, B, dB, c, s);
-}
 }  // namespace rfb

@@ -158,15 +158,4 @@ __global__ void __launch_bounds__((W / 2) * (1 << LOGN) / 16, 512 / ((W / 2) * (
     PairBody<LOGN, W>::run(g, stw, reinterpret_cast<float4 *>(smem_raw_p2p));
 }
 
-// The same body compiled for MINB resident CTAs per SM (fewer registers per thread, a few spilled values): the pure-copy
-// probe (csrc/probe.cu) reaches 92-100 % of the HBM copy peak with this access pattern at 4 CTAs/SM, the transform 78-80 %:
-// the exchange/butterfly phases take a CTA off the memory system for ~1/5 of its time, which a fifth CTA would cover.
-// ptxas: MINB = 5 -> 96 registers, 44 bytes spilled; MINB = 6 -> 80 registers, 344 bytes.  RFB200_LF_CTAS selects it.
-template <int LOGN, int W, int MINB>
-__global__ void __launch_bounds__((W / 2) * (1 << LOGN) / 16, MINB)
-    fft_pow2_pair_kernel_occ(const TileGeom<float> g, const float2 *__restrict__ stw) {
-    extern __shared__ __align__(16) unsigned char smem_raw_p2po[];
-    PairBody<LOGN, W>::run(g, stw, reinterpret_cast<float4 *>(smem_raw_p2po));
-}
-
 }  // namespace rfb

@@ -71,23 +71,13 @@ struct TileGeom {
     uint32_t g_mul, c_mul, pre_bound, post_bound;
     const cx<T> *pre_tab, *post_tab;
     int pre_swap, post_swap;
-};
-
-// control block of the fused four-step kernel (pow2_fused4_kernel.cuh)
-struct Fuse4Ctl {
-    uint32_t nstrips;        // strips in total (outer batch x strips per outer item)
-    uint32_t cols, cw;       // neighbouring lines per outer item / per strip (the last strip of an item may be narrower)
-    uint32_t tiles;          // tiles per strip and step
-    uint32_t ring, lag;      // scratch slots; distance (in strips) between A(s) and B(s) in the ticket order
-    FastDiv d_tiles, d_spo, d_ring;  // item -> (unit, tile); strip -> (outer, strip within outer item); strip -> slot
-    int64_t in_outer, in_strip, out_outer, out_strip;  // byte offsets on the array side
-    int64_t slot_bytes;
-    uint32_t *ctr;           // [0] ticket, [1] error flag, [2 .. 2+S) tiles of A(s) done, [2+S .. 2+2S) tiles of B(s) done
+    // tables of the DCT / DST load / store modes (line_io.cuh)
+    const cx<T> *aux_ld, *aux_st;
 };
 
 // Ticket order of the fused four-step kernel: unit u of 2*S units -> (step, strip).  A(0) .. A(lag-1), then the pairs
 // A(lag + i), B(i), then the last lag B's.  B(s) depends on A(s); A(s), s >= ring, on B(s - ring).  With ring > lag every
-// unit comes after the units it depends on (checked on the host by tests/test_abi.py through rfb200_debug_fuse4_unit).
+// unit comes after the units it depends on (checked on the host by tests/test_abi.py through rfb200_debug_fuse4_unit; used by fused4v2_kernel.cuh).
 __host__ __device__ inline bool fuse4_decode_unit(uint32_t unit, uint32_t S, uint32_t lag, bool &stepB, uint32_t &strip) {
     if (unit >= 2 * S) return false;
     if (unit < lag) { stepB = false; strip = unit; }
@@ -129,7 +119,54 @@ __device__ __forceinline__ uint32_t padidx(uint32_t e, uint32_t sh) { return e +
 // deliver spectrum bin f (all store modes); line_io.cuh's store_value works by output slot
 template <typename T, bool ALIGNED>
 __device__ __forceinline__ void store_bin_value(int mode, int flags, char *line, int64_t sa, uint32_t f, uint32_t n,
-                                                cx<T> val) {
+                                                cx<T> val, const cx<T> *__restrict__ aux = nullptr) {
+    auto put = [&](uint32_t i, T r) { *reinterpret_cast<T *>(line + (int64_t)i * sa) = r; };
+    const bool sine = (flags & FLAG_SINE) != 0, ortho = (flags & FLAG_ORTHO) != 0;
+    switch (mode) {
+        case ST_G_DCT1: {
+            const uint32_t N = n / 2 + 1;
+            if (f >= N) return;
+            put(f, (ortho && (f == 0 || f == N - 1)) ? val.x * T(0.70710678118654752) : val.x);
+            return;
+        }
+        case ST_G_DST1: {
+            const uint32_t N = n / 2 - 1;
+            if (f < 1 || f > N) return;
+            put(f - 1, -val.y);
+            return;
+        }
+        case ST_G_DCT2: {
+            // ortho scales one output by 1/sqrt 2: index 0 (cosine); sine: the caller's index 0 as the reference does
+            // (H:3033-3034) or, without FLAG_QUIRK, N-1 as SciPy does
+            const uint32_t N = n, k = sine ? N - 1 - f : f, scaled = sine ? ((flags & FLAG_QUIRK) ? 0u : N - 1) : 0u;
+            const cx<T> w = __ldg(aux + f);
+            T r = T(2) * (w.x * val.x - w.y * val.y);
+            if (ortho && k == scaled) r *= T(0.70710678118654752);
+            put(k, r);
+            return;
+        }
+        case ST_G_DCT3: {
+            const uint32_t N = n, idx = f < (N + 1) / 2 ? 2 * f : 2 * (N - 1 - f) + 1;
+            put(idx, (sine && (idx & 1)) ? -val.x : val.x);
+            return;
+        }
+        case ST_G_DCT4: {
+            const uint32_t N = 2 * n;
+            const cx<T> w = cmul(val, __ldg(aux + 4 * f));  // aux: exp(-2 pi i t / (8N)); exp(-i pi f / N)
+            put(2 * f, T(2) * w.x);
+            put(N - 1 - 2 * f, sine ? T(2) * w.y : T(-2) * w.y);  // sine: (-1)^k with k = N-1-2f odd
+            return;
+        }
+        case ST_G_DCT4Z: {
+            const uint32_t N = n / 2;
+            if (f >= N) return;
+            const cx<T> w = __ldg(aux + (2 * f + 1));  // aux: exp(-2 pi i t / (8N))
+            const T r = T(2) * (w.x * val.x - w.y * val.y);
+            put(f, (sine && (f & 1)) ? -r : r);
+            return;
+        }
+        default: break;
+    }
     switch (mode) {
         case ST_HALF:
             if (2 * f > n) return;
@@ -224,7 +261,7 @@ __device__ __forceinline__ void run_pass(const TileGeom<T> &g, const TileCtx &cx
             for (uint32_t m = 0; m < Rr; ++m) {
                 C val = mk<T>(T(0), T(0));
                 if (ok) {
-                    val = load_value<T, ALIGNED>(g.load_mode, g.flags, line, g.in_sa, e0 + ido * m, n, g.n_in);
+                    val = load_value<T, ALIGNED>(g.load_mode, g.flags, line, g.in_sa, e0 + ido * m, n, g.n_in, g.aux_ld);
                     if (g.backward) val = cswap(val);
                 }
                 v[m] = val;
@@ -255,7 +292,7 @@ __device__ __forceinline__ void run_pass(const TileGeom<T> &g, const TileCtx &cx
                 }
                 val = cscale(val, g.fct);
                 if (g.backward) val = cswap(val);
-                store_bin_value<T, ALIGNED>(g.store_mode, g.flags, line, g.out_sa, f, n, val);
+                store_bin_value<T, ALIGNED>(g.store_mode, g.flags, line, g.out_sa, f, n, val, g.aux_st);
             }
         } else {
             C *base = buf + (size_t)w * pitch;

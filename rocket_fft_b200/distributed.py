@@ -81,10 +81,10 @@ class SlabFFTN:
                 self.peer_recv = [self.hdl.get_buffer(h, blk, dtype) for h in range(P)]
                 self.streams = [torch.cuda.Stream(device=device) for _ in range(min(P, 4))]
                 self.mode = "symm"
-                n1_ok = (n1 & (n1 - 1)) == 0 and 16 <= n1 <= 16384
+                n1_ok = (n1 & (n1 - 1)) == 0 and 16 <= n1 <= 2048  # lengths the strided power-of-two kernel takes
                 if exchange == "fused" or (exchange == "auto" and n1_ok and local_c2c_is_default):
                     if not n1_ok:
-                        raise ValueError("fused exchange needs a power-of-two axis-1 length (16..16384)")
+                        raise ValueError("fused exchange needs a power-of-two axis-1 length (16..2048)")
                     self.mode = "fused"
             except Exception as e:  # pragma: no cover - depends on the box
                 if exchange in ("symm", "fused"):

@@ -137,6 +137,11 @@ def _scipy_extras(overwrite_x, workers, plan=None):
 # ---------------------------------------------------------------------------------------------
 # argument normalisation
 # ---------------------------------------------------------------------------------------------
+def _arr(x):
+    """Array-likes that numpy / scipy accept (lists, tuples, scalars) become NumPy arrays; arrays and tensors pass."""
+    return x if hasattr(x, "shape") and hasattr(x, "dtype") else np.asarray(x)
+
+
 def _shape_axes(x, s, axes, default_all):
     nd = len(x.shape)
     if axes is None:
@@ -210,6 +215,7 @@ def _fct(shape, axes, norm, forward, delta=None):
 # complex / real transforms
 # ---------------------------------------------------------------------------------------------
 def _c2cn(x, s, axes, norm, forward, default_all):
+    x = _arr(x)
     s, axes = _shape_axes(x, s, axes, default_all)
     dt = _np_dtype(x)
     cdt = _cplx_of(dt)
@@ -231,6 +237,7 @@ def _c2cn(x, s, axes, norm, forward, default_all):
 
 
 def _r2cn(x, s, axes, norm, forward, default_all):
+    x = _arr(x)
     dt = _np_dtype(x)
     if _is_complex(dt):
         raise TypeError(f"unsupported dtype {dt}")
@@ -252,6 +259,7 @@ def _r2cn(x, s, axes, norm, forward, default_all):
 
 
 def _c2rn(x, s, axes, norm, forward, default_all):
+    x = _arr(x)
     s_given = s is not None
     s, axes = _shape_axes(x, s, axes, default_all)
     cdt = _cplx_of(_np_dtype(x))
@@ -374,6 +382,7 @@ def ihfftn(x, s=None, axes=None, norm=None, overwrite_x=False, workers=None, *, 
 # DCT / DST
 # ---------------------------------------------------------------------------------------------
 def _r2rn(x, type, s, axes, norm, orthogonalize, forward, cosine, default_all):
+    x = _arr(x)
     type = int(type)
     if type not in (1, 2, 3, 4):
         raise ValueError("Invalid type; must be one of (1, 2, 3, 4).")
@@ -383,7 +392,15 @@ def _r2rn(x, type, s, axes, norm, orthogonalize, forward, cosine, default_all):
         type = {1: 1, 2: 3, 3: 2, 4: 4}[type]
     delta = (-1.0 if cosine else 1.0) if type == 1 else 0.0
     ortho = (norm == "ortho") if orthogonalize is None else bool(orthogonalize)
-    fn = _ll.dct if cosine else _ll.dst
+    if cosine:
+        fn = _ll.dct
+    elif ortho and type in (2, 3):
+        # this layer follows scipy.fft: DST-II/III under ortho scale element N-1 (the reference's low-level dst scales
+        # element 0 -- a known quirk it warns about, README.md:61-65; the numba_* drop-in symbols keep it)
+        def fn(a, o, ax, t, f, orth):
+            return _ll.dst(a, o, ax, t, f, orth, dst_ortho="scipy")
+    else:
+        fn = _ll.dst
     if _is_complex(dt):
         cdt = _cplx_of(dt)
         x = _pad_or_crop(x, s, axes, cdt)

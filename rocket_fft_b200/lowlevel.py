@@ -30,7 +30,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("RFB200_LIB") or os.path.join(_HERE, "librocketfft_b200.so")
+LIB_PATH = os.path.join(_HERE, "librocketfft_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -64,6 +64,10 @@ _c.rfb200_version.restype = C.c_char_p
 _c.rfb200_launch_count.restype = C.c_uint64
 _c.rfb200_set_stream.argtypes = [C.c_void_p]
 _c.rfb200_set_dst_ortho_quirk.argtypes = [C.c_int]
+_c.rfb200_failure_count.restype = C.c_uint64
+_c.rfb200_plan_cache_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+_c.rfb200_host_dst.restype = None
+_c.rfb200_host_dst.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_int]
 
 
 class TransformError(RuntimeError):
@@ -120,11 +124,34 @@ def set_stream(stream) -> None:
         _c.rfb200_set_stream(C.c_void_p(int(stream)))
 
 
-def _current_stream() -> int:
+def failure_count() -> int:
+    """Number of numba_* calls that failed since the library was loaded (those entry points return void: a failed call
+    prints its reason, fills a host output with NaN and bumps this counter)."""
+    return int(_c.rfb200_failure_count())
+
+
+def plan_cache_stats():
+    """(entries, bytes) of the device table cache (all devices)."""
+    e, b = C.c_uint64(0), C.c_uint64(0)
+    _c.rfb200_plan_cache_stats(C.byref(e), C.byref(b))
+    return int(e.value), int(b.value)
+
+
+def _current_stream(a=None) -> int:
+    """The caller's current stream ON THE DEVICE THAT HOLDS `a` (torch tensors; other exporters: the current device's)."""
     torch = sys.modules.get("torch")
     if torch is not None and torch.cuda.is_available():
+        dev = getattr(a, "device", None)
+        if dev is not None and getattr(dev, "type", None) == "cuda":
+            return int(torch.cuda.current_stream(dev).cuda_stream)
         return int(torch.cuda.current_stream().cuda_stream)
     return 0
+
+
+def _same_device(*arrays):
+    devs = {str(a.device) for a in arrays if getattr(getattr(a, "device", None), "type", None) == "cuda"}
+    if len(devs) > 1:
+        raise ValueError(f"arrays live on different devices: {sorted(devs)}")
 
 
 def _is_host(a) -> bool:
@@ -161,9 +188,10 @@ def _device_call(op, ain, aout, axes, mid):
     A = (C.c_int64 * max(nd, 1))
     shape_c, sin_c, sout_c = A(*shape), A(*st_in), A(*st_out)
     axes_c = (C.c_uint64 * max(len(ax), 1))(*ax)
+    _same_device(ain, aout)
     rc = getattr(_c, "rfb200_" + op)(
         prec, nd, shape_c, sin_c, sout_c, len(ax), axes_c, *mid, C.c_void_p(pin), C.c_void_p(pout),
-        C.c_void_p(_current_stream()),
+        C.c_void_p(_current_stream(ain)),
     )
     if rc != 0:
         raise TransformError(last_error())
@@ -210,10 +238,33 @@ def dct(ain, aout, axes, type, fct, ortho, nthreads=1):
     return _call("dct", ain, aout, axes, (type, fct, ortho, nthreads), (int(type), float(fct), int(bool(ortho))))
 
 
-def dst(ain, aout, axes, type, fct, ortho, nthreads=1):
+def dst(ain, aout, axes, type, fct, ortho, nthreads=1, *, dst_ortho=None):
+    """`dst_ortho` chooses the DST-II/III scaling under ortho=True for THIS call: None = the process-wide setting
+    (set_dst_ortho_quirk; default: the reference's, which scales element 0, README.md:61-65), "scipy" = element N-1 as
+    SciPy does, "reference" = the reference's."""
     if int(type) not in (1, 2, 3, 4):
         raise ValueError("invalid DST type")
-    return _call("dst", ain, aout, axes, (type, fct, ortho, nthreads), (int(type), float(fct), int(bool(ortho))))
+    if dst_ortho not in (None, "scipy", "reference"):
+        raise ValueError("dst_ortho must be None, 'scipy' or 'reference'")
+    if dst_ortho is None or not ortho:
+        return _call("dst", ain, aout, axes, (type, fct, ortho, nthreads), (int(type), float(fct), int(bool(ortho))))
+    if _is_host(ain) != _is_host(aout):
+        raise TypeError("input and output must both be host arrays or both be device arrays")
+    if not _is_host(ain):
+        return _device_call("dst", ain, aout, axes, (int(type), float(fct), 2 if dst_ortho == "scipy" else 3))
+    _check("dst", ain, aout)
+    nd = len(_abi.describe(ain)[1])
+    if len(_abi.describe(aout)[1]) != nd:
+        raise ValueError("Input and output array must have the same number of dimensions")
+    rin, k1 = _abi.make_record(ain)
+    rout, k2 = (rin, k1) if aout is ain else _abi.make_record(aout)
+    rax, k3 = _abi.axes_record(axes)
+    _c.rfb200_host_dst(nd, C.addressof(rin), C.addressof(rout), C.addressof(rax), int(type), float(fct), 1,
+                       0 if dst_ortho == "scipy" else 1)
+    err = last_error()
+    if err:
+        raise TransformError(err)
+    return aout
 
 
 def r2r_separable_hartley(ain, aout, axes, fct, nthreads=1):
@@ -253,7 +304,7 @@ def c2c_scatter(ain, parts, axis, forward, fct):
     A = (C.c_int64 * nd)
     ptrs = (C.c_void_p * len(parts))(*[d[0] for d in desc])
     rc = _c.rfb200_c2c_scatter(prec, nd, A(*shp), A(*st_in), A(*st_out), int(axis) % nd, int(bool(forward)), float(fct),
-                               C.c_void_p(pin), len(parts), ptrs, C.c_void_p(_current_stream()))
+                               C.c_void_p(pin), len(parts), ptrs, C.c_void_p(_current_stream(ain)))
     if rc != 0:
         raise TransformError(last_error())
     return parts
@@ -292,7 +343,7 @@ def _pad_call(op, ain, aout, shape, axes, forward, fct):
     A = (C.c_int64 * max(nd, 1))
     rc = getattr(_c, "rfb200_" + op)(
         prec, nd, A(*shp_in), A(*shape), A(*st_in), A(*st_out), len(ax), (C.c_uint64 * max(len(ax), 1))(*ax),
-        int(bool(forward)), float(fct), C.c_void_p(pin), C.c_void_p(pout), C.c_void_p(_current_stream()),
+        int(bool(forward)), float(fct), C.c_void_p(pin), C.c_void_p(pout), C.c_void_p(_current_stream(ain)),
     )
     if rc != 0:
         raise TransformError(last_error())
@@ -328,7 +379,7 @@ def roll(ain, aout, shift):
         raise ValueError("roll: one shift per dimension")
     A = (C.c_int64 * max(nd, 1))
     rc = _c.rfb200_roll(int(item), nd, A(*shp_in), A(*st_in), A(*st_out), A(*sh), C.c_void_p(pin), C.c_void_p(pout),
-                        C.c_void_p(_current_stream()))
+                        C.c_void_p(_current_stream(ain)))
     if rc != 0:
         raise TransformError(last_error())
     return aout
@@ -361,7 +412,7 @@ def scale_lines(data, table):
         return data
     prec = 0 if dt in (np.dtype(np.float32), np.dtype(np.complex64)) else 1
     rc = _c.rfb200_scale_lines(prec, int(dt in _CPLX), total // n, n, C.c_void_p(pt), C.c_void_p(pd),
-                               C.c_void_p(_current_stream()))
+                               C.c_void_p(_current_stream(data)))
     if rc != 0:
         raise TransformError(last_error())
     return data

@@ -96,3 +96,26 @@ def test_fused_fourstep_ticket_order_never_puts_a_consumer_first():
                     if s >= ring:
                         assert pos[(1, s - ring)] < pos[(0, s)], (S, lag, ring, s)
     assert f(0, 2, 3) == -1
+
+
+def test_transform_without_a_gpu_fails_loudly():
+    """There is no CPU fallback: on a machine without a CUDA device a numba_* call must not return silently with an
+    untouched output -- the message is readable, the host output is NaN, the failure is counted."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import rocket_fft_b200 as R
+
+    before = R.failure_count()
+    x = np.ones((4, 16), dtype=np.complex64)
+    y = np.zeros((6, 16), dtype=np.complex64)[::2, ::2]  # strided output: only its own elements may be touched
+    x2 = x[:3, :8]
+    with pytest.raises(R.TransformError):
+        R.c2c(x2, y, [1], True, 1.0)
+    assert R.failure_count() == before + 1 and R.last_error()
+    assert np.isnan(y.real).all() and np.isnan(y.imag).all()
+    full = y.base
+    assert (full[1::2] == 0).all() and (full[:, 1::2] == 0).all()
+    assert R.good_size(1000003, False) == 1000188  # the host-only function still works

@@ -115,7 +115,8 @@ class _ReferenceBackend:
     def dct(self, a, o, axes, type, fct, ortho):
         return self.ref.dct(a, o, list(axes), type, fct, ortho, 1)
 
-    def dst(self, a, o, axes, type, fct, ortho):
+    def dst(self, a, o, axes, type, fct, ortho, dst_ortho=None):
+        # (the reference has one DST-II/III ortho scaling -- its own; the SciPy one exists only in the CUDA library)
         return self.ref.dst(a, o, list(axes), type, fct, ortho, 1)
 
 

@@ -17,13 +17,16 @@ pytestmark = pytest.mark.gpu
 DST = os.path.join(parity.ROOT, "baseline", "_ref")
 EXT = sysconfig.get_config_var("EXT_SUFFIX")
 
-# reference test files exercised here (fork-based and cache-subprocess tests are left out:
-# CUDA contexts do not survive fork())
-# Default: the direct C-ABI tests (~75 s).  RFB200_FULL_REFERENCE_SUITE=1 adds the np.fft / scipy.fft grids
-# (3016 + 172 + 82 + 14 tests, ~5 more minutes); round-1 log of the full run: profiles/r01_reference_suite_on_gpu.log
-FILES = ["test_low_level_interface.py", "test_overwrite_and_dtype.py", "test_numpy_like.py"]
+# The reference's test files run by default (about 6 minutes on the B200 box): the direct C-ABI tests, the np.fft /
+# scipy.fft comparison grids (3016 + 172 + 82 + 14 tests), NumPy's own suite as the reference vendors it, threading,
+# and the on-disk JIT-cache test (which re-runs the library in fresh processes).  Left out: test_multiprocessing.py -- it
+# transforms in the parent and then in a fork()ed Pool, and a CUDA context does not survive fork(): the children get the
+# library's "forked after CUDA was used" error (tests/test_gpu_robustness.py pins that behaviour).
+# RFB200_FULL_REFERENCE_SUITE=1 adds SciPy's vendored suite, FFTLog, the scipy-like policy and typing files.
+FILES = ["test_low_level_interface.py", "test_overwrite_and_dtype.py", "test_numpy_like.py", "test_numpy_compare.py",
+         "test_scipy_compare.py", "test_numpy_testsuite.py", "test_misc.py", "test_multithreading.py", "test_caching.py"]
 if os.environ.get("RFB200_FULL_REFERENCE_SUITE"):
-    FILES += ["test_numpy_compare.py", "test_scipy_compare.py", "test_numpy_testsuite.py", "test_misc.py", "test_multithreading.py"]
+    FILES += ["test_scipy_testsuite.py", "test_fftlog.py", "test_scipy_like.py", "test_typing.py"]
 
 
 @pytest.mark.parametrize("fname", FILES)

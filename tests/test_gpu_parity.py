@@ -449,7 +449,7 @@ def test_slab_pipeline_emulated_on_one_device(R):
 
     T = trusted()
     dev = torch.device("cuda:0")
-    for shape, ranks in (((128, 128, 128), (2, 8)), ((64, 1024, 96), (2, 4, 8)), ((16, 16384, 8), (4,))):
+    for shape, ranks in (((128, 128, 128), (2, 8)), ((64, 1024, 96), (2, 4, 8)), ((16, 2048, 8), (4,))):
         n0, n1, n2 = shape
         fullh = cplx(np.random.default_rng(21), shape, np.complex64)
         want = np.empty_like(fullh)
@@ -466,6 +466,63 @@ def test_slab_pipeline_emulated_on_one_device(R):
                 R.c2c(y, y, [0], True, 1.0)
                 torch.cuda.synchronize()
                 check(y.cpu().numpy(), want[:, h * (n1 // P):(h + 1) * (n1 // P)], np.float32, n0 * n1 * n2, ("slab emulation", shape, P, h))
+
+
+def _dcst_fft_len(kind, typ, N):
+    """Length of the complex transform a DCT / DST line of N points is folded into (ops.cu op_dcst)."""
+    if typ == 1:
+        return 2 * (N - 1) if kind == "dct" else 2 * (N + 1)
+    if typ in (2, 3):
+        return N
+    return N // 2 if N % 2 == 0 else 2 * N
+
+
+def _largest_prime(n):
+    p, f = 1, 2
+    while f * f <= n:
+        while n % f == 0:
+            p, n = f, n // f
+        f += 1
+    return max(p, n) if n > 1 else p
+
+
+def test_dct_dst_one_launch_per_axis_and_no_work_area(R):
+    """Every DCT / DST type, odd and even lengths, runs as ONE kernel launch per transformed axis (the type's reordering,
+    extension and phase factors are the load / store stage of the line transform; reference: T_dct1 H:2918-2955, T_dst1
+    H:2957-2985, T_dcst23 H:2987-3061, T_dcst4 H:3063-3163) -- against the reference, float64 and float32, strided axes,
+    ortho on and off."""
+    import torch
+
+    T = trusted()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(31)
+    for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        for shape, axes in (((6, 100), [1]), ((5, 101), [1]), ((1000, 12), [0]), ((33, 64, 10), [0, 1]), ((4, 2048), [1]),
+                            ((3, 2049), [1]), ((2047, 5), [0]), ((7, 2), [1]), ((2, 3, 4), [0, 1, 2])):
+            x = rng.standard_normal(shape).astype(dt)
+            d_x = torch.from_numpy(x).to(dev)
+            for kind in ("dct", "dst"):
+                for typ in (1, 2, 3, 4):
+                    for ortho in (False, True):
+                        want = np.empty_like(x)
+                        getattr(T, kind)(x, want, axes, typ, 0.5, ortho)
+                        d_y = torch.empty_like(d_x)
+                        R.launch_count_reset()
+                        getattr(R, kind)(d_x, d_y, axes, typ, 0.5, ortho)
+                        torch.cuda.synchronize()
+                        if all(_largest_prime(_dcst_fft_len(kind, typ, shape[a])) <= 64 for a in axes):
+                            # (a transform length with a prime factor above 64 -- e.g. DST-I of 100 points, 2 * 101 -- is a
+                            # Bluestein line and keeps the work-area path)
+                            assert R.launch_count() == len(axes), (kind, typ, shape, R.launch_count())
+                        n = 1
+                        for a in axes:
+                            n *= 4 * shape[a]
+                        check(d_y.cpu().numpy(), want, dt, n, (kind, typ, shape, ortho, dt))
+                        # in place
+                        d_z = d_x.clone()
+                        getattr(R, kind)(d_z, d_z, axes, typ, 0.5, ortho)
+                        torch.cuda.synchronize()
+                        check(d_z.cpu().numpy(), want, dt, n, (kind, typ, shape, ortho, dt, "in place"))
 
 
 def test_numba_njit_calls_run_on_the_gpu(R):
@@ -645,7 +702,7 @@ def test_long_real_lines_two_transforms_per_thread(R):
 
 def test_fused_fourstep_long_strided_lines(R):
     """16384-point complex64 lines along a strided axis of arrays larger than the L2 cache: both four-step passes run
-    in one persistent kernel with the intermediate in an L2-resident scratch ring (fused4v2_kernel.cuh, pow2_fused4_kernel.cuh).  Widths that
+    in one persistent kernel with the intermediate in an L2-resident scratch ring (fused4v2_kernel.cuh).  Widths that
     are not multiples of the strip / tile width, a batch of arrays, in place and out of place, both directions,
     fct != 1 -- against the reference on the host."""
     import torch
@@ -654,14 +711,15 @@ def test_fused_fourstep_long_strided_lines(R):
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(12)
     n = 16384
-    # RFB200_FUSE4 (read per call): 2 = warp-specialised fused kernel (default), 1 = round-1 fused kernel, 0 = two launches
-    os.environ["RFB200_FUSE4_CHECK"] = "1"
+    # RFB200_FUSE4 (read per call): unset / 1 = the fused kernel (default), 0 = two launches
     try:
-        for mode in ("2", "1", "0"):
+        for mode in ("1", "0"):
             os.environ["RFB200_FUSE4"] = mode
-            R.launch_count_reset()
+            R.launch_trace(True)
             _fused_fourstep_cases(R, T, dev, rng, n)
-            assert R.launch_count() > 0
+            names = R.launch_trace_get()
+            R.launch_trace(False)
+            assert any("fused2" in k for k in names) == (mode == "1"), names[:6]
     finally:
         os.environ.pop("RFB200_FUSE4", None)
     _fused_fourstep_cases(R, T, dev, rng, n)
@@ -670,7 +728,7 @@ def test_fused_fourstep_long_strided_lines(R):
 def _fused_fourstep_cases(R, T, dev, rng, n):
     import torch
 
-    for shape, axis in (((n, 777), 0), ((2, n, 800), 1), ((n, 1025), 0)):
+    for shape, axis in (((n, 777), 0), ((2, n, 800), 1), ((n, 1025), 0), ((3, n, 545), 1)):
         xh = cplx(rng, shape, np.complex64)
         x = torch.from_numpy(xh).to(dev)
         for fwd, fct, inplace in ((True, 1.0, False), (False, 0.5, True)):

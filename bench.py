@@ -480,12 +480,12 @@ def bench_fftn(args, R, torch, dist, dev, rank, world, barrier, max_over_ranks):
         del v, V
     else:
         ft = torch.from_numpy(full).to(dev) if rank == 0 else torch.empty(pn, pn, pn, dtype=torch.complex64, device=dev)
-        dist.broadcast(ft, 0)
+        dist.broadcast(torch.view_as_real(ft), 0)  # (NCCL has no complex type: the same bytes as pairs of floats)
         lo, hi = shard_batch(pn, rank, world)
         plan = SlabFFTN((pn, pn, pn), torch.complex64, dev)
         y = plan.forward(ft[lo:hi].clone(), True, 1.0).contiguous()  # (pn, pn/P, pn): axis 1 sharded
         parts = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
-        dist.gather(y, parts, dst=0)
+        dist.gather(torch.view_as_real(y), [torch.view_as_real(q) for q in parts] if rank == 0 else None, dst=0)
         got = torch.cat(parts, dim=1).cpu().numpy() if rank == 0 else None
         res["exchange_engine"] = plan.mode
         del ft, y, parts, plan

@@ -1,7 +1,9 @@
 // C ABI of librocketfft_b200.so: the ten numba_* drop-in symbols and the rfb200_* device entry
 // points declared in include/rocketfft_b200.h.
 #include <math.h>
+#include <fcntl.h>
 #include <pthread.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -114,6 +116,18 @@ void fill_nan_host(const rfb200_array_record *aout, uint64_t ndim, const std::ve
     }
 }
 
+// Is [p, p + n) ordinary writable host memory?  Asked without CUDA (the forked child must not call it) and without a
+// signal handler: read(2) from /dev/zero into the range fails with EFAULT instead of faulting.  (Overwrites the range
+// with zeros -- only used on an output that is about to be filled with NaN.)
+bool host_writable(void *p, size_t n) {
+    if (!p) return false;
+    const int fd = open("/dev/zero", O_RDONLY);
+    if (fd < 0) return false;
+    const ssize_t r = read(fd, p, n);
+    close(fd);
+    return r == (ssize_t)n;
+}
+
 enum OpKind { OP_C2C, OP_R2C, OP_C2R, OP_C2C_SYM, OP_DCT, OP_DST, OP_FFTPACK, OP_SEP_HARTLEY, OP_GEN_HARTLEY };
 
 struct OpFlags {
@@ -181,7 +195,6 @@ void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb2
     int64_t fail_item = 0, fail_scalar = 4;
     bool out_on_host = false;
     try {
-        enter_call();
         NdArgs a;
         const rfb200_array_record *shp_src = (k == OP_C2R) ? aout : ain;
         a.shape.assign(shp_src->shape_and_strides, shp_src->shape_and_strides + ndim);
@@ -208,6 +221,8 @@ void run_record_op(OpKind k, uint64_t ndim, const rfb200_array_record *ain, rfb2
         fail_shape = shape_out;
         fail_item = out_item;
         fail_scalar = ssz;
+        if (g_forked_child.load()) out_on_host = host_writable(aout->data, (size_t)ssz);  // (no CUDA query in the child)
+        enter_call();
         const bool dev_in = is_device_ptr(ain->data), dev_out = is_device_ptr(aout->data);
         out_on_host = !dev_out;
         if (dev_in != dev_out) { set_error("input and output must both be host or both be device arrays"); throw Error(); }

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <stdlib.h>
@@ -456,6 +457,7 @@ static void run_norm(const LineJob &job, const std::vector<Dim> &dims, cudaStrea
     const bool simple = (job.load_mode == LD_C2C || job.load_mode == LD_REAL) && job.store_mode == ST_C2C &&
                         job.flags == 0 && (job.n_in == 0 || job.n_in == job.n);
     const size_t esz = job.prec ? 16 : 8;
+    if (launch_pow2_stream_f32(job, dims, s)) return;
     // power-of-two lines: register-resident Stockham kernel
     static const bool use_pow2 = env_int("RFB200_NO_POW2", 0) == 0;
     if (use_pow2 && alignment_ok(job, dims)) {
@@ -551,7 +553,7 @@ static void run_via_scratch(const LineJob &job, const std::vector<Dim> &dims, cu
     RFB_AFTER_LAUNCH();
 }
 
-static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s, void *work = nullptr);
 
 static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
     uint64_t n1, n2;
@@ -564,12 +566,16 @@ static void run_fourstep(const LineJob &job, const std::vector<Dim> &dims, cudaS
     run_fourstep_plain(job, dims, s);
 }
 
-static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s) {
+static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s, void *work) {
     const int64_t esz = job.prec ? 16 : 8;
     uint64_t n1, n2;
     choose_split(job.n, job.prec, n1, n2);
     const uint64_t L = total_lines(dims);
-    Scratch sc(L * job.n * (uint64_t)esz, s);
+    std::unique_ptr<Scratch> own;
+    if (!work) {
+        own.reset(new Scratch(L * job.n * (uint64_t)esz, s));
+        work = own->p;
+    }
     // Scratch layout: when the lines are strided (neighbouring lines adjacent in memory) the
     // scratch keeps that neighbour dim fastest, [..][n][dim0], so that both steps read and write
     // rows of adjacent lines; contiguous lines use [..][dim0][n].
@@ -596,7 +602,7 @@ static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims,
     for (size_t i = 0; i < dims.size(); ++i) A.batch.push_back(Dim{dims[i].n, dims[i].is, sstr[i], false});
     A.batch.push_back(Dim{(int64_t)n2, job.is, s_axis, true});
     A.in = job.in;
-    A.out = (char *)sc.p;
+    A.out = (char *)work;
     A.backward = job.backward;
     A.fct = 1.0;
     A.load_mode = job.load_mode;
@@ -616,7 +622,7 @@ static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims,
     B.os = (int64_t)n1 * job.os;
     for (size_t i = 0; i < dims.size(); ++i) B.batch.push_back(Dim{dims[i].n, sstr[i], dims[i].os, false});
     B.batch.push_back(Dim{(int64_t)n1, (int64_t)n2 * s_axis, job.os, job.post_tab != nullptr});
-    B.in = (const char *)sc.p;
+    B.in = (const char *)work;
     B.out = job.out;
     B.backward = job.backward;
     B.fct = job.fct;

@@ -148,6 +148,8 @@ bool launch_pow2_f32(const LineJob &job, const std::vector<Dim> &dims, bool load
 bool launch_pow2_f64(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, cudaStream_t s);
 // fused4v2_launch.cu: both four-step passes of 16384-point strided complex64 lines in one warp-specialised persistent kernel
 bool launch_fourstep_fused2_f32(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
+// pow2_stream_launch.cu: strided 512 / 1024-point complex64 lines, persistent kernel fed by the copy engine
+bool launch_pow2_stream_f32(const LineJob &job, const std::vector<Dim> &dims, cudaStream_t s);
 // jit.cu: run-time specialised kernel for smooth non-power-of-two lengths (NVRTC); false if not taken
 bool launch_spec_jit(const LineJob &job, const std::vector<Dim> &dims, bool load_lf, bool store_lf, bool aligned,
                      cudaStream_t s);

@@ -2,6 +2,7 @@
 // Semantics follow the reference's public templates (_pocketfft_hdronly.h:3875-4091) and
 // its boundary file (_pocketfft_numba.cpp:25-223); see SURVEY.md section 8(a).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,24 +52,32 @@ static uint64_t prod(const std::vector<int64_t> &s) {
 // c2c  (reference: c2c H:3875-3889 -> general_nd H:3568-3607: axes in the given order,
 // first axis reads `in`, later ones work on `out`; fct applied once)
 // ---------------------------------------------------------------------------------------
+static void c2c_one_axis(int prec, const std::vector<int64_t> &shape, const std::vector<int64_t> &si,
+                         const std::vector<int64_t> &sout, size_t ax, const char *in, char *out, bool forward, double fct,
+                         cudaStream_t s) {
+    LineJob j;
+    j.prec = prec;
+    j.n = (uint64_t)shape[ax];
+    j.in = in;
+    j.out = out;
+    j.is = si[ax];
+    j.os = sout[ax];
+    j.batch = batch_dims(shape, si, sout, ax);
+    j.backward = !forward;
+    j.fct = fct;
+    run_lines(j, s);
+}
+
+// (Measured and dropped, profiles/r02l_l2_blocked_axis_groups.log: running the passes over axes (1, 2) of a 1024^3 volume slice
+// group by slice group -- 16 / 32 / 64 MiB at a time, so that the second pass finds its input in L2 -- is SLOWER than two
+// full walks, 12.6 / 10.5 / 9.5 ms against 7.2 ms: a strided-lines tile occupies an SM for ~9 us and a slice group is
+// only 3.5 waves of them; the launches' ramps and tails cost more than the saved HBM round trip.)
 static void c2c_axes(int prec, const std::vector<int64_t> &shape, const std::vector<int64_t> &sin,
                      const std::vector<int64_t> &sout, const uint64_t *axes, size_t naxes, const char *in, char *out,
                      bool forward, double fct, cudaStream_t s) {
     bool first = true;
     for (size_t i = 0; i < naxes; ++i) {
-        const size_t ax = (size_t)axes[i];
-        LineJob j;
-        j.prec = prec;
-        j.n = (uint64_t)shape[ax];
-        j.in = first ? in : out;
-        j.out = out;
-        const auto &si = first ? sin : sout;
-        j.is = si[ax];
-        j.os = sout[ax];
-        j.batch = batch_dims(shape, si, sout, ax);
-        j.backward = !forward;
-        j.fct = first ? fct : 1.0;
-        run_lines(j, s);
+        c2c_one_axis(prec, shape, first ? sin : sout, sout, (size_t)axes[i], first ? in : out, out, forward, first ? fct : 1.0, s);
         first = false;
     }
 }

@@ -9,6 +9,7 @@
 //   * downloads are unstaged by a background thread, so that the caller goes on uploading the next chunk: both directions
 //     of the link stay busy, as with pinned memory.
 // (The reference has no counterpart: its arrays never leave the host.)
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -86,8 +87,15 @@ class CopyPool {
     bool stop_ = false;
 };
 
-constexpr size_t SLOT_BYTES = 32u << 20;
+// Ring geometry and copy threads.  Measured on the B200 box (tools/host_copy_probe.py, profiles/r02l_host_copy_probe.log):
+// memcpy pageable -> pinned 14 GB/s with one thread, 42 GB/s with 8, 49 GB/s with 12, 28 GB/s with 16 (of 16 cores); the
+// link does 54 GB/s per direction.  RFB200_STAGE_THREADS / RFB200_STAGE_SLOT_MB override.
 constexpr int NSLOTS = 4;
+inline int env_or(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && atoi(e) > 0) ? atoi(e) : dflt;
+}
+const size_t SLOT_BYTES = (size_t)env_or("RFB200_STAGE_SLOT_MB", 32) << 20;
 
 struct Slot {
     char *p = nullptr;
@@ -111,7 +119,7 @@ struct Stager::Impl {
     bool stop = false;
     std::atomic<bool> failed{false};
 
-    Impl() : pool(std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 2))) {
+    Impl() : pool(env_or("RFB200_STAGE_THREADS", std::max(2, std::min(12, (int)std::thread::hardware_concurrency() * 3 / 4)))) {
         for (int i = 0; i < NSLOTS; ++i) {
             RFB_CUDA_CHECK(cudaHostAlloc((void **)&up[i].p, SLOT_BYTES, cudaHostAllocDefault));
             RFB_CUDA_CHECK(cudaHostAlloc((void **)&down[i].p, SLOT_BYTES, cudaHostAllocDefault));

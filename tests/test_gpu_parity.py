@@ -753,6 +753,67 @@ def _fused_fourstep_cases(R, T, dev, rng, n):
     assert float(wide[:, :7].abs().max()) == 0.0 and float(wide[:, 808:].abs().max()) == 0.0
 
 
+def test_streamed_strided_lines_512_1024(R):
+    """512- and 1024-point complex64 lines along a strided axis with enough tiles to fill the device: the persistent kernel
+    fed by the copy engine, two warp groups sharing one exchange buffer (pow2_stream_kernel.cuh) -- full and partial tiles,
+    one and two batch dims, in place and out of place, both directions, fct != 1, different pitches on the two sides --
+    against the reference on the host; RFB200_STREAM=0 (other process) is covered by test_strided_lines_two_per_thread."""
+    import torch
+
+    T = trusted()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(21)
+    for shape, axis in (((2, 1024, 4800), 1), ((2, 1024, 4808), 1), ((3, 1024, 3200), 1), ((2, 512, 4808), 1), ((5, 512, 1936), 1),
+                        ((2, 1024, 3, 1616), 1)):
+        n = shape[axis]
+        xh = cplx(rng, shape, np.complex64)
+        x = torch.from_numpy(xh).to(dev)
+        for fwd, fct, inplace in ((True, 1.0, False), (False, 0.5, True)):
+            want = np.empty_like(xh)
+            T.c2c(xh, want, [axis], fwd, fct)
+            src = x.clone()
+            out = src if inplace else torch.empty_like(src)
+            R.launch_trace(True)
+            R.c2c(src, out, [axis], fwd, fct)
+            torch.cuda.synchronize()
+            names = R.launch_trace_get()
+            R.launch_trace(False)
+            assert len(names) == 1 and "stream" in names[0], names
+            check(out.cpu().numpy(), want, np.float32, n, ("streamed lines", shape, fwd, inplace))
+            if not inplace:
+                assert torch.equal(src, x)
+    # a wider output array (different pitch), untouched outside the written columns
+    xh = cplx(rng, (2, 1024, 4800), np.complex64)
+    x = torch.from_numpy(xh).to(dev)
+    wide = torch.zeros(2, 1024, 4900, dtype=torch.complex64, device=dev)
+    R.c2c(x, wide[:, :, 50:4850], [1], True, 1.0)
+    torch.cuda.synchronize()
+    want = np.empty_like(xh)
+    T.c2c(xh, want, [1], True, 1.0)
+    check(wide[:, :, 50:4850].cpu().numpy(), want, np.float32, 1024, "streamed lines, different pitches")
+    assert float(wide[:, :, :50].abs().max()) == 0.0 and float(wide[:, :, 4850:].abs().max()) == 0.0
+    # rows more than 64 KiB apart stay on the register kernel (the copy engine is slow when every row lies on its own page)
+    xh = cplx(rng, (1024, 9610), np.complex64)
+    x = torch.from_numpy(xh).to(dev)
+    R.launch_trace(True)
+    R.c2c(x, x, [0], True, 1.0)
+    torch.cuda.synchronize()
+    names = R.launch_trace_get()
+    R.launch_trace(False)
+    assert len(names) == 1 and "pair" in names[0], names
+    want = np.empty_like(xh)
+    T.c2c(xh, want, [0], True, 1.0)
+    check(x.cpu().numpy(), want, np.float32, 1024, "far-strided lines")
+    # 1024^3-like volume slice: all three axes of (64, 1024, 1024) through the N-D driver
+    xh = cplx(rng, (64, 1024, 1024), np.complex64)
+    x = torch.from_numpy(xh).to(dev)
+    want = np.empty_like(xh)
+    T.c2c(xh, want, [0, 1, 2], True, 1.0)
+    R.c2c(x, x, [0, 1, 2], True, 1.0)
+    torch.cuda.synchronize()
+    check(x.cpu().numpy(), want, np.float32, 64 * 1024 * 1024, "volume (64, 1024, 1024)")
+
+
 def test_strided_lines_two_per_thread(R):
     """float32 lines of 128..1024 points along a strided axis (neighbouring lines adjacent): the kernel that keeps two
     lines per thread (pow2_pair_kernel.cuh) -- odd and even numbers of lines, partial tiles, extra batch dims on either

@@ -80,8 +80,36 @@ def cfg3():
     run(f"cfg3 fftn c64 {n}^3 (whole)", lambda: R.c2c(v, V, [0, 1, 2], True, 1.0), nb, 5 * n**3 * 3 * math.log2(n), 3)
     for ax in (0, 1, 2):
         run(f"     axis {ax}", lambda: R.c2c(v, V, [ax], True, 1.0), nb, None, 3)
+    run("     axes (1,2)", lambda: R.c2c(v, V, [1, 2], True, 1.0), nb, None, 3)
+    run("     in place (whole)", lambda: R.c2c(V, V, [0, 1, 2], True, 1.0), nb, None, 3)
+    # host time to enqueue the whole call (launch-bound if it approaches the device time)
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    R.c2c(v, V, [0, 1, 2], True, 1.0)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print(f"     host enqueue time of one call: {(t1 - t0) * 1e3:.3f} ms", flush=True)
     ms = timeit(lambda: torch.fft.fftn(v), 3)
     report("     cuFFT fftn [side ref]", ms, nb)
+    del v, V
+
+
+def batch2d():
+    x = torch.randn(64, 2048, 2048, dtype=torch.complex64, device=dev)
+    y = torch.empty_like(x)
+    nb = 2 * x.numel() * 8
+    run("fft2 c64 64 x (2048,2048)", lambda: R.c2c(x, y, [1, 2], True, 1.0), nb, None, 3)
+    run("     in place", lambda: R.c2c(y, y, [1, 2], True, 1.0), nb, None, 3)
+    ms = timeit(lambda: torch.fft.fft2(x), 3)
+    report("     cuFFT fft2 [side ref]", ms, nb)
+    del x, y
+    x = torch.randn(256, 1024, 1024, dtype=torch.complex64, device=dev)
+    y = torch.empty_like(x)
+    nb = 2 * x.numel() * 8
+    run("fft2 c64 256 x (1024,1024)", lambda: R.c2c(x, y, [1, 2], True, 1.0), nb, None, 3)
+    ms = timeit(lambda: torch.fft.fft2(x), 3)
+    report("     cuFFT fft2 [side ref]", ms, nb)
 
 
 def cfg4():
@@ -139,7 +167,7 @@ def nonpow2():
     report("   cuFFT irfft2 [side ref]", ms, nb)
 
 
-ALL = {"nonpow2": nonpow2, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "sizes": sizes}
+ALL = {"batch2d": batch2d, "nonpow2": nonpow2, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "sizes": sizes}
 if __name__ == "__main__":
     names = [a for a in sys.argv[1:] if a in ALL] or ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"]
     print(R.version(), torch.cuda.get_device_name(0))

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round 2, session k: whole GPU test-suite after the DCT/DST test fix, smoke(), default bench line.
+set -u
+O=gpurun_out
+mkdir -p $O
+( time timeout 2400 python -m pytest tests/ -x -q -m gpu --durations=15 ) > $O/r2k_pytest_gpu.log 2>&1
+tail -30 $O/r2k_pytest_gpu.log
+( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > $O/r2k_smoke.log 2>&1
+tail -4 $O/r2k_smoke.log
+( time timeout 900 python bench.py ) > $O/r2k_bench.json 2> $O/r2k_bench.err
+tail -c 3000 $O/r2k_bench.json; tail -5 $O/r2k_bench.err

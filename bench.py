@@ -170,6 +170,33 @@ def run_reference_arm(args, world):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Multi-rank runs: keep this rank's threads (and therefore the first touch of its pinned host buffers) on the NUMA node
+    its GPU hangs off, so that eight ranks do not push their H2D / D2H traffic through one node's memory.  Best effort:
+    returns what was found for the JSON line."""
+    info = {"numa_node": None, "cpus_bound": None}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        info["cpus_allowed"] = len(allowed)
+        mine = cpus & allowed
+        if mine and mine != allowed:
+            os.sched_setaffinity(0, mine)
+            info["cpus_bound"] = len(mine)
+    except Exception as e:  # pragma: no cover - depends on the box
+        info["error"] = repr(e)[:80]
+    return info
+
+
 def rel_l2(a, b):
     import numpy as np
 
@@ -211,6 +238,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.images
@@ -384,6 +412,8 @@ def main():
         e2e["h2d_GBps"] = h2d_b / e2e["h2d_ms"] / 1e6
         e2e["d2h_GBps"] = d2h_b / e2e["d2h_ms"] / 1e6
         e2e["frac_of_copy_only"] = e2e["copy_only_ms"] / e2e["ms_per_step"]
+        if numa is not None:
+            e2e["numa_binding_rank0"] = numa
         del hx, hX, nx, nX
         # the drop-in case: plain (pageable) NumPy arrays, as an @njit caller has them
         try:

@@ -184,6 +184,12 @@ uint64_t rfb200_failure_count(void);
  * RFB200_PLAN_CACHE_MB (default 1024) MiB; least recently used tables are released beyond that (reference: the 16-entry
  * LRU plan cache, _pocketfft_hdronly.h:3169-3223). */
 void rfb200_plan_cache_stats(uint64_t *entries, uint64_t *bytes);
+/* Page-locks (cudaHostRegister) / releases a range of host memory the caller owns, e.g. the buffer of a NumPy array that
+ * numba_* calls will use many times: such calls then move their data at the rate of pinned memory (no staging copy).  The
+ * caller keeps the range alive and unpins it before freeing it -- which is why the library does not do this on its own
+ * behind a cache: it cannot see free() / munmap().  0 on success, non-zero + rfb200_last_error otherwise. */
+int rfb200_host_pin(void *ptr, uint64_t bytes);
+int rfb200_host_unpin(void *ptr);
 /* numba_dst with an explicit choice of the DST-II/III scaling under ortho (quirk: 1 = the reference's, which scales
  * element 0, _pocketfft_hdronly.h:3033-3039; 0 = SciPy's, element N-1), whatever rfb200_set_dst_ortho_quirk says.
  * rfb200_dst takes the same choice in its `ortho` argument: 0 off, 1 on (process-wide choice), 2 on/SciPy, 3 on/reference. */

@@ -21,6 +21,7 @@ from .lowlevel import (  # noqa: F401
     launch_trace,
     launch_trace_get,
     lib,
+    pinned,
     plan_cache_clear,
     plan_cache_stats,
     r2c,

@@ -600,6 +600,29 @@ RFB_EXPORT const char *rfb200_launch_trace_get(void) {
 RFB_EXPORT void rfb200_launch_count_reset(void) { rfb::launch_count_reset(); }
 RFB_EXPORT void rfb200_set_dst_ortho_quirk(int enabled) { rfb::set_dst_ortho_quirk(enabled != 0); }
 RFB_EXPORT uint64_t rfb200_failure_count(void) { return g_failures.load(); }
+RFB_EXPORT int rfb200_host_pin(void *ptr, uint64_t bytes) {
+    clear_error();
+    try {
+        enter_call();
+        if (!ptr || !bytes) { set_error("rfb200_host_pin: empty range"); throw Error(); }
+        RFB_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+        return 0;
+    } catch (const Error &) {
+    } catch (const std::exception &e) { set_error(e.what()); }
+    cudaGetLastError();
+    return 1;
+}
+RFB_EXPORT int rfb200_host_unpin(void *ptr) {
+    clear_error();
+    try {
+        enter_call();
+        RFB_CUDA_CHECK(cudaHostUnregister(ptr));
+        return 0;
+    } catch (const Error &) {
+    } catch (const std::exception &e) { set_error(e.what()); }
+    cudaGetLastError();
+    return 1;
+}
 RFB_EXPORT void rfb200_plan_cache_stats(uint64_t *entries, uint64_t *bytes) { rfb::plan_cache_stats(entries, bytes); }
 // host-array variant of numba_dst with an explicit DST-II/III ortho scaling (quirk: 0 SciPy's, 1 the reference's)
 RFB_EXPORT void rfb200_host_dst(uint64_t ndim, const rfb200_array_record *ain, rfb200_array_record *aout, rfb200_array_record *axes,

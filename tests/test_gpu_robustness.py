@@ -168,3 +168,36 @@ def test_dst_ortho_scaling_per_call():
         assert parity.l2err(F.idst(x, t, norm="ortho"), scipy.fft.idst(x, t, norm="ortho")) < 1e-12
         assert parity.l2err(F.dstn(x, t, norm="ortho"), scipy.fft.dstn(x, t, norm="ortho")) < 1e-12
     assert np.allclose(F.fft([1.0, 2.0, 3.0]), np.fft.fft([1.0, 2.0, 3.0]))  # array-likes are accepted
+
+
+def test_caller_pinned_numpy_arrays():
+    """rfb200_host_pin / rocket_fft_b200.pinned: NumPy arrays page-locked by the caller go through the host path without the
+    staging ring and give the same result; pinning the same range twice is an error that leaves the first pin intact."""
+    out = _run(
+        """
+        import numpy as np, rocket_fft_b200 as R
+        from oracle import pocketfft_oracle as O
+        rng = np.random.default_rng(3)
+        x = rng.standard_normal((8, 1 << 20)).astype(np.float32)     # 32 MiB: above the staging threshold
+        got = np.empty((8, (1 << 19) + 1), dtype=np.complex64)
+        want = np.empty_like(got)
+        O.r2c(x, want, [1], True, 1.0)
+        with R.pinned(x, got):
+            R.r2c(x, got, [1], True, 1.0)
+            err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+            try:
+                with R.pinned(x):
+                    print("second pin succeeded")
+            except R.TransformError as e:
+                print("second pin refused:", str(e)[:60])
+            got[...] = 0
+            R.r2c(x, got, [1], True, 1.0)
+            err = max(err, float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+        got[...] = 0
+        R.r2c(x, got, [1], True, 1.0)                                 # pageable again: the staging ring
+        err = max(err, float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+        print("err", err)
+        assert err < 1e-5 * 20
+        """
+    )
+    assert "err" in out and "refused" in out, out

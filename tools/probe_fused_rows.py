@@ -13,8 +13,11 @@ import rocket_fft_b200 as R
 from tools.microbench import timeit
 
 dev = torch.device("cuda:0")
-for shape, axis in (((16384, 8193), 0), ((31, 16384, 264), 1), ((8, 16384, 1025), 1)):
-    x = torch.randn(*shape, dtype=torch.complex64, device=dev)
+for shape, axis in (((16384, 8193), 0), ((31, 16384, 264), 1), ((8, 16384, 1025), 1), ((16384, 8193, 8196), 0), ((16384, 8192, 8192), 0)):
+    if len(shape) == 3 and axis == 0:  # (rows, columns used, row pitch in elements): a view with 32-byte aligned rows
+        x = torch.randn(shape[0], shape[2], dtype=torch.complex64, device=dev)[:, :shape[1]]
+    else:
+        x = torch.randn(*shape, dtype=torch.complex64, device=dev)
     R.launch_trace(True)
     R.c2c(x, x, [axis], True, 1.0)
     torch.cuda.synchronize()

@@ -342,6 +342,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom[2][0] if dom[2] else None, "kernels_of_one_step": step_names,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[0],
+                    # the same launch on the bytes it really moved through HBM (ncu): how close the kernel runs to the copy peak
+                    "frac_on_traffic": (traffic / (dom[0] * 1e-3) / 1e9) / peak if traffic else None,
                     "whole_step_frac_of_compulsory": (B * alg_bytes_per_image() / (ms_per_step * 1e-3) / 1e9) / peak}
         # ---- parity of the timed path against the reference's CPU result of the same input (image 0) -------
         try:

@@ -236,13 +236,16 @@ bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
     set_prefetch_by_mode<float>(g, job, dims, (uint32_t)W);
     const float2 *stw = (const float2 *)get_table(TAB_STOCKHAM, job.prec, 1ull << LOGN, 0);
     const size_t smem = (size_t)Body::WP * Body::PITCH * sizeof(float4);
-    void (*kern)(const TileGeom<float>, const float2 *) = fft_pow2_pair_kernel<LOGN, W>;
-    static thread_local int dev_set = -1;
+    // 16-byte accesses when everything is a multiple of 16 bytes (the half spectrum of rfft2, rows of 8193 points, is not)
+    bool al16 = (((uintptr_t)job.in | (uintptr_t)job.out | (uintptr_t)job.is | (uintptr_t)job.os) & 15) == 0;
+    for (size_t d = 1; d < dims.size(); ++d) al16 = al16 && ((dims[d].is | dims[d].os) & 15) == 0;
+    void (*kern)(const TileGeom<float>, const float2 *) = al16 ? fft_pow2_pair_kernel<LOGN, W, true> : fft_pow2_pair_kernel<LOGN, W, false>;
+    static thread_local int dev_set[2] = {-1, -1};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev_set != dev) {
+    if (dev_set[al16] != dev) {
         RFB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dev_set = dev;
+        dev_set[al16] = dev;
     }
     kern<<<(unsigned)ntiles, Body::NT, smem, s>>>(g, stw);
     {

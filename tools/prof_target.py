@@ -32,6 +32,9 @@ elif name == "rfft2":
 elif name == "cfg3":
     x = torch.randn(512, 1024, 1024, dtype=torch.complex64, device=dev)
     fn = lambda: R.c2c(x, x, [0, 1, 2], True, 1.0)
+elif name == "cfg3_axis0":
+    x = torch.randn(1024, 512, 1024, dtype=torch.complex64, device=dev)  # 1024-point lines, rows 4 MiB apart
+    fn = lambda: R.c2c(x, x, [0], True, 1.0)
 elif name == "cfg4a":
     x = torch.randn(4096, 15015, dtype=torch.complex64, device=dev)
     y = torch.empty_like(x)

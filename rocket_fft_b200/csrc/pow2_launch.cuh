@@ -162,8 +162,9 @@ inline int lf_mode() {
 inline bool lf_plain_job(const LineJob &job, const std::vector<Dim> &dims) {
     const int64_t e = (int64_t)sizeof(float2);
     if (dims.empty() || dims[0].is != e || dims[0].os != e || (dims[0].tw && job.twN)) return false;
+    // (scatter output -- the fused transform + NVLink push of the slab fftn -- included: the store picks its buffer per bin)
     return job.load_mode == LD_C2C && job.store_mode == ST_C2C && !job.flags && (job.n_in == 0 || job.n_in == job.n) &&
-           !job.pre_tab && !job.post_tab && job.split_out.empty() && !job.conv;
+           !job.pre_tab && !job.post_tab && !job.conv;
 }
 
 template <typename T, int LOGN>
@@ -239,6 +240,7 @@ bool launch_pair_inst(const LineJob &job, const std::vector<Dim> &dims, cudaStre
     // 16-byte accesses when everything is a multiple of 16 bytes (the half spectrum of rfft2, rows of 8193 points, is not)
     bool al16 = (((uintptr_t)job.in | (uintptr_t)job.out | (uintptr_t)job.is | (uintptr_t)job.os) & 15) == 0;
     for (size_t d = 1; d < dims.size(); ++d) al16 = al16 && ((dims[d].is | dims[d].os) & 15) == 0;
+    for (auto sp : job.split_out) al16 = al16 && ((uintptr_t)sp & 15) == 0;
     void (*kern)(const TileGeom<float>, const float2 *) = al16 ? fft_pow2_pair_kernel<LOGN, W, true> : fft_pow2_pair_kernel<LOGN, W, false>;
     static thread_local int dev_set[2] = {-1, -1};
     int dev = 0;

@@ -152,10 +152,13 @@ struct PairBody {
                 va = cscale(va, f);
                 vb = cscale(vb, f);
                 if (bw) { va = cswap(va); vb = cswap(vb); }
-                if (AL16 && ok1) *reinterpret_cast<float4 *>(pq) = make_float4(va.x, va.y, vb.x, vb.y);
+                char *dst = pq;
+                // fused exchange (rfb200_c2c_scatter): the bin's block decides which (peer) buffer receives it
+                if (g.split_blk) dst = g.split_base[fdiv((uint32_t)(t + j * TPL + q * (N / RL)), g.d_split)] + (pq - g.out);
+                if (AL16 && ok1) *reinterpret_cast<float4 *>(dst) = make_float4(va.x, va.y, vb.x, vb.y);
                 else {
-                    *reinterpret_cast<C *>(pq) = va;
-                    if (ok1) *reinterpret_cast<C *>(pq + sizeof(C)) = vb;
+                    *reinterpret_cast<C *>(dst) = va;
+                    if (ok1) *reinterpret_cast<C *>(dst + sizeof(C)) = vb;
                 }
                 pq += step_q;
             }

@@ -126,7 +126,7 @@ bool launch_fourstep_fused2_f32(const LineJob &job, const std::vector<Dim> &dims
         return false;
     // 6 strips between the two steps of a strip, a ring of 10 slots (40 MiB): measured against 3 / 6 and 8 / 14
     // (profiles/r02c_fuse4v2_tma_sweep.log); the tiles of about 7 strips are in flight at any time.
-    const int lag_d = 6, ring_d = 10;
+    static const int lag_d = env_i("RFB200_FUSE4_LAG", 6), ring_d = env_i("RFB200_FUSE4_RING", 10);  // (sweep: profiles/r02z_fuse4v2_ring_lag.log)
     F4v2Params p;
     memset(&p, 0, sizeof(p));
     p.nstrips = (uint32_t)S;

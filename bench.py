@@ -579,7 +579,54 @@ def bench_fftn(args, R, torch, dist, dev, rank, world, barrier, max_over_ranks):
                                          "fused": " (the axis-1 FFT kernel stores straight into peer HBM over NVLink; alltoall_ms = that kernel incl. its butterflies)"}[plan.mode],
                 "layout": "result left axis-1 sharded (transposed); transpose_back available",
                 "limiter": max(st, key=st.get)})
+    del x, plan
+    torch.cuda.empty_cache()
+    try:
+        res["rfftn"] = bench_rfftn_slab(args, R, torch, dist, dev, rank, world, timed)
+    except Exception as e:  # pragma: no cover
+        res["rfftn"] = {"error": repr(e)}
     return res
+
+
+def bench_rfftn_slab(args, R, torch, dist, dev, rank, world, timed):
+    """rfftn of a real float32 n^3 volume, slab-decomposed (SlabRFFTN: r2c along the last axis, then the complex pipeline on the
+    half spectrum, fused transform + push): total ms, and parity of the same path at 256^3 against the reference."""
+    import numpy as np
+
+    from rocket_fft_b200.distributed import SlabRFFTN, shard_batch
+
+    n = args.fftn_n
+    out = {"workload": f"rfftn float32 {n}^3 (r2c axes=[0,1,2]), slab-decomposed over {world} GPUs"}
+    pn = min(256, n)
+    full = torch.empty(pn, pn, pn, dtype=torch.float32, device=dev)
+    if rank == 0:
+        full.copy_(torch.from_numpy(np.random.default_rng(3).standard_normal((pn, pn, pn), dtype=np.float32)))
+    dist.broadcast(full, 0)
+    lo, hi = shard_batch(pn, rank, world)
+    plan = SlabRFFTN((pn, pn, pn), torch.float32, dev)
+    y = plan.forward(full[lo:hi].contiguous()).contiguous()
+    parts = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
+    dist.gather(torch.view_as_real(y), [torch.view_as_real(q) for q in parts] if rank == 0 else None, dst=0)
+    if rank == 0:
+        ref, kind, cores = reference_lib()
+        fh = full.cpu().numpy()
+        want = np.empty((pn, pn, pn // 2 + 1), dtype=np.complex64)
+        ref.r2c(fh, want, [0, 1, 2], True, 1.0, cores)
+        err = rel_l2(torch.cat(parts, dim=1).cpu().numpy(), want)
+        bound = 1e-5 * math.log2(pn**3)
+        out.update({"parity_rel_l2": err, "parity_bound": bound, "parity_ok": bool(err <= bound),
+                    "parity_case": f"{pn}^3 through the same path vs oracle/_ref ({kind})"})
+    del plan, y, parts, full
+    torch.cuda.empty_cache()
+    plan = SlabRFFTN((n, n, n), torch.float32, dev)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    x = torch.randn(n // world, n, n, dtype=torch.float32, device=dev, generator=g)
+    for _ in range(3):
+        plan.forward(x)
+    ms = timed(lambda: plan.forward(x), max(3, min(args.steps, 10)))
+    out.update({"ms": ms, "exchange_engine": plan.mode, "bytes_sent_per_gpu": plan.bytes_sent_per_rank,
+                "GFLOPs": 2.5 * n**3 * math.log2(n**3) / ms / 1e6})
+    return out
 
 
 def bench_other_configs(R, torch, dev, timeit):

@@ -62,6 +62,14 @@ class SlabFFTN:
         self.local_in_shape = (n0 // P, n1, n2)
         self.local_out_shape = (n0, n1 // P, n2)
         blk = (P, n0 // P, n1 // P, n2)
+        # Peer-mapped receive buffers are the plan's own: their rows are padded to a multiple of 128 bytes, so that the kernels
+        # that write and read them (the fused transform + push, the axis-0 pass) see 16-byte aligned rows whatever n2 is --
+        # the half spectrum of a real volume has n2/2 + 1 = 513 points per row (measured: rfftn 1024^3 on two GPUs 7.0 -> see
+        # profiles/README.md).  The NCCL engine keeps dense buffers (all_to_all_single wants them contiguous).
+        esz = torch.empty((), dtype=dtype).element_size()
+        per128 = max(1, 128 // esz)
+        self.n2_alloc = -(-n2 // per128) * per128
+        blk_alloc = (P, n0 // P, n1 // P, self.n2_alloc)
         self.bytes_sent_per_rank = n0 // P * n1 * n2 * torch.empty((), dtype=dtype).element_size() * (P - 1) // P
         # Exchange engine.  "fused": symm buffers + the axis-1 transform writes its output
         # straight into the peers' receive buffers (rfb200_c2c_scatter): transform and all-to-all
@@ -75,10 +83,11 @@ class SlabFFTN:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
 
-                self.recv = symm_mem.empty(blk, dtype=dtype, device=device)
+                self.recv_alloc = symm_mem.empty(blk_alloc, dtype=dtype, device=device)
+                self.recv = self.recv_alloc[..., :n2]
                 gname = (group if group is not None else dist.group.WORLD).group_name
-                self.hdl = symm_mem.rendezvous(self.recv, gname)
-                self.peer_recv = [self.hdl.get_buffer(h, blk, dtype) for h in range(P)]
+                self.hdl = symm_mem.rendezvous(self.recv_alloc, gname)
+                self.peer_recv = [self.hdl.get_buffer(h, blk_alloc, dtype)[..., :n2] for h in range(P)]
                 self.streams = [torch.cuda.Stream(device=device) for _ in range(min(P, 4))]
                 self.mode = "symm"
                 n1_ok = (n1 & (n1 - 1)) == 0 and 16 <= n1 <= 2048  # lengths the strided power-of-two kernel takes
@@ -92,7 +101,8 @@ class SlabFFTN:
                 self.symm_error = repr(e)
                 self.hdl = None
         if self.mode == "nccl":
-            self.recv = torch.empty(blk, dtype=dtype, device=device)
+            self.n2_alloc = n2
+            self.recv_alloc = self.recv = torch.empty(blk, dtype=dtype, device=device)
             self.send = torch.empty(blk, dtype=dtype, device=device)
         self.timings = {}
 
@@ -154,7 +164,8 @@ class SlabFFTN:
 
     def local_axis0(self, forward=True):
         """recv viewed as (n0, n1/P, n2): transform along axis 0 in place."""
-        y = self.recv.view(self.local_out_shape)
+        n0, n1p, n2 = self.local_out_shape
+        y = self.recv_alloc.view(n0, n1p, self.n2_alloc)[..., :n2]
         self.c2c(y, y, [0], forward, 1.0)
         return y
 
@@ -172,7 +183,7 @@ class SlabFFTN:
         P = self.P
         n0, n1p, n2 = self.local_out_shape
         # second exchange (NCCL): block (h -> g) = axis-0 range of g x my axis-1 range
-        send = y.view(P, n0 // P, n1p, n2).clone()
+        send = y.reshape(P, n0 // P, n1p, n2).contiguous()
         back = self.torch.empty_like(send)
         self.dist.all_to_all_single(back.view(-1), send.view(-1), group=self.group)
         # back[h, i0, j, i2] holds X[i0, h*n1/P + j, i2]
@@ -215,7 +226,10 @@ class SlabRFFTN:
                               exchange=exchange)
         self.P, self.rank = self.inner.P, self.inner.rank
         self.torch = torch
-        self.spec = torch.empty((n0 // self.P, n1, self.n2h), dtype=self.cdtype, device=device)
+        # (rows of the half spectrum padded to 128 bytes like the receive buffers)
+        self.n2h_alloc = self.inner.n2_alloc if self.inner.mode != "nccl" else self.n2h
+        self.spec_alloc = torch.empty((n0 // self.P, n1, self.n2h_alloc), dtype=self.cdtype, device=device)
+        self.spec = self.spec_alloc[..., :self.n2h]
         self.bytes_sent_per_rank = self.inner.bytes_sent_per_rank
 
     @property
@@ -248,7 +262,7 @@ class SlabRFFTN:
             send = send.contiguous()
         back = self.torch.empty_like(send)
         inner.dist.all_to_all_single(back.view(-1), send.view(-1), group=inner.group)
-        self.spec.view(n0 // P, P, n1p, self.n2h).copy_(back.permute(1, 0, 2, 3))
+        self.spec_alloc.view(n0 // P, P, n1p, self.n2h_alloc)[..., :self.n2h].copy_(back.permute(1, 0, 2, 3))
         if out is None:
             out = self.torch.empty((n0 // P, n1, n2), dtype=self.rdtype, device=self.spec.device)
         self.c2r(self.spec, out, [1, 2], forward, fct)                # c2c along axis 1, Hermitian -> real along 2

@@ -49,7 +49,8 @@ static std::vector<int64_t> c_strides(const std::vector<int64_t> &shape, int64_t
 // `bytes` receives the allocation size.
 static std::vector<int64_t> c_strides_padded(const std::vector<int64_t> &shape, int64_t esz, uint64_t &bytes) {
     std::vector<int64_t> padded = shape;
-    if (!shape.empty() && shape.back() * esz >= 1024) {
+    static const bool no_pad = [] { const char *e = getenv("RFB200_NO_PADDED_SCRATCH"); return e && atoi(e) != 0; }();  // (A/B aid)
+    if (!no_pad && !shape.empty() && shape.back() * esz >= 1024) {
         const int64_t per = 128 / esz;
         padded.back() = (shape.back() + per - 1) / per * per;
     }
@@ -150,12 +151,31 @@ static void r2c_into(int prec, const std::vector<int64_t> &shape_in, const std::
     j.fct = fct;
     j.load_mode = LD_REAL;
     j.store_mode = ST_HALF;
-    run_lines(j, s);
-    if (axes.size() > 1) {
-        std::vector<int64_t> shape_out = shape_in;
-        shape_out[L] = shape_in[L] / 2 + 1;
-        c2c_axes(prec, shape_out, sout, sout, axes.data(), axes.size() - 1, out, out, forward, 1.0, s);
+    std::vector<int64_t> shape_out = shape_in;
+    shape_out[L] = shape_in[L] / 2 + 1;
+    // Three or more axes on a dense output whose rows are not multiples of 128 bytes (513 points for a 1024-point real axis):
+    // the passes between the real transform and the last one would walk that array in place along strided axes with every
+    // row at another 8-byte phase.  They run on a scratch copy with padded rows instead (c_strides_padded); the last pass
+    // reads the scratch and writes the caller's array.  (Same arithmetic, same order of the axes.)
+    const int64_t esz = prec ? 16 : 8;
+    static const bool no_pad = [] { const char *e = getenv("RFB200_NO_PADDED_SCRATCH"); return e && atoi(e) != 0; }();  // (A/B aid)
+    const bool padded_path = !no_pad && axes.size() >= 3 && L + 1 == shape_out.size() && sout[L] == esz && (shape_out[L] * esz) % 128 != 0 &&
+                             shape_out[L] * esz >= 1024;
+    if (padded_path) {
+        uint64_t tbytes = 0;
+        const std::vector<int64_t> st = c_strides_padded(shape_out, esz, tbytes);
+        Scratch tmp(tbytes, s);
+        j.out = (char *)tmp.p;
+        j.os = st[L];
+        j.batch = batch_dims(shape_in, sin, st, L);
+        run_lines(j, s);
+        const size_t nc = axes.size() - 1;  // complex passes
+        c2c_axes(prec, shape_out, st, st, axes.data(), nc - 1, (const char *)tmp.p, (char *)tmp.p, forward, 1.0, s);
+        c2c_one_axis(prec, shape_out, st, sout, (size_t)axes[nc - 1], (const char *)tmp.p, out, forward, 1.0, s);
+        return;
     }
+    run_lines(j, s);
+    if (axes.size() > 1) c2c_axes(prec, shape_out, sout, sout, axes.data(), axes.size() - 1, out, out, forward, 1.0, s);
 }
 
 void op_r2c(const NdArgs &a, bool forward, cudaStream_t s) {

@@ -814,6 +814,30 @@ def test_streamed_strided_lines_512_1024(R):
     check(x.cpu().numpy(), want, np.float32, 64 * 1024 * 1024, "volume (64, 1024, 1024)")
 
 
+def test_r2c_three_axes_goes_through_the_padded_scratch(R):
+    """r2c over three (and four) axes whose half-spectrum rows are >= 1 KiB and not a multiple of 128 bytes: the passes between
+    the real transform and the last one run on a scratch copy with padded rows (ops.cu r2c_into) -- against the reference,
+    float32 and float64, repeated axes included; and the c2r way back (padded temporary)."""
+    T = trusted()
+    rng = np.random.default_rng(41)
+    for dt in (np.float32, np.float64):
+        for shape, axes in (((24, 40, 300), [0, 1, 2]), ((6, 20, 24, 258), [1, 2, 3]), ((24, 40, 300), [1, 0, 2]),
+                            ((16, 24, 300), [2, 0, 1, 2]), ((3, 8, 12, 1026), [0, 1, 2, 3])):
+            x = rng.standard_normal(shape).astype(dt)
+            oshape = list(shape)
+            oshape[axes[-1]] = shape[axes[-1]] // 2 + 1
+            want = np.zeros(oshape, dtype=CD[dt])
+            got = np.zeros(oshape, dtype=CD[dt])
+            T.r2c(x, want, axes, True, 0.5)
+            R.r2c(x, got, axes, True, 0.5)
+            n = int(np.prod([shape[a] for a in set(axes)]))
+            check(got, want, dt, n, ("r2c padded scratch", shape, axes, dt))
+            back_w, back_g = np.empty_like(x), np.empty_like(x)
+            T.c2r(want, back_w, axes, False, 1.0)
+            R.c2r(want, back_g, axes, False, 1.0)
+            check(back_g, back_w, dt, n, ("c2r padded temporary", shape, axes, dt))
+
+
 def test_strided_lines_two_per_thread(R):
     """float32 lines of 128..1024 points along a strided axis (neighbouring lines adjacent): the kernel that keeps two
     lines per thread (pow2_pair_kernel.cuh) -- odd and even numbers of lines, partial tiles, extra batch dims on either

@@ -167,7 +167,18 @@ def nonpow2():
     report("   cuFFT irfft2 [side ref]", ms, nb)
 
 
-ALL = {"batch2d": batch2d, "nonpow2": nonpow2, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "sizes": sizes}
+def rfftn():
+    x = torch.randn(1024, 1024, 1024, dtype=torch.float32, device=dev)
+    X = torch.empty(1024, 1024, 513, dtype=torch.complex64, device=dev)
+    nb = x.numel() * 4 + X.numel() * 8
+    run("rfftn f32 1024^3 (r2c axes=[0,1,2])", lambda: R.r2c(x, X, [0, 1, 2], True, 1.0), nb, None, 3)
+    y = torch.empty_like(x)
+    run("irfftn (c2r axes=[0,1,2])", lambda: R.c2r(X, y, [0, 1, 2], False, 1.0), nb, None, 3)
+    ms = timeit(lambda: torch.fft.rfftn(x), 3)
+    report("     cuFFT rfftn [side ref]", ms, nb)
+
+
+ALL = {"rfftn": rfftn, "batch2d": batch2d, "nonpow2": nonpow2, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "sizes": sizes}
 if __name__ == "__main__":
     names = [a for a in sys.argv[1:] if a in ALL] or ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"]
     print(R.version(), torch.cuda.get_device_name(0))

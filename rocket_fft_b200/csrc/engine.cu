@@ -570,27 +570,29 @@ static void run_fourstep_plain(const LineJob &job, const std::vector<Dim> &dims,
     const int64_t esz = job.prec ? 16 : 8;
     uint64_t n1, n2;
     choose_split(job.n, job.prec, n1, n2);
-    const uint64_t L = total_lines(dims);
-    std::unique_ptr<Scratch> own;
-    if (!work) {
-        own.reset(new Scratch(L * job.n * (uint64_t)esz, s));
-        work = own->p;
-    }
     // Scratch layout: when the lines are strided (neighbouring lines adjacent in memory) the
     // scratch keeps that neighbour dim fastest, [..][n][dim0], so that both steps read and write
-    // rows of adjacent lines; contiguous lines use [..][dim0][n].
+    // rows of adjacent lines -- rows padded to a multiple of 128 bytes (with 8193 neighbouring lines dense rows would each
+    // start at another 8-byte phase: no 16-byte accesses, every row segment straddling one more sector);
+    // contiguous lines use [..][dim0][n].
     const bool lf = !dims.empty() && (iabs64(dims[0].is) < iabs64(job.is) || iabs64(dims[0].os) < iabs64(job.os));
     std::vector<int64_t> sstr(dims.size());
     int64_t s_axis, acc;
     if (lf) {
         sstr[0] = esz;
         s_axis = dims[0].n * esz;
+        if (!work && s_axis >= 1024) s_axis = (s_axis + 127) & ~(int64_t)127;
         acc = s_axis * (int64_t)job.n;
         for (size_t i = 1; i < dims.size(); ++i) { sstr[i] = acc; acc *= dims[i].n; }
     } else {
         s_axis = esz;
         acc = (int64_t)job.n * esz;
         for (size_t i = 0; i < dims.size(); ++i) { sstr[i] = acc; acc *= dims[i].n; }
+    }
+    std::unique_ptr<Scratch> own;
+    if (!work) {
+        own.reset(new Scratch((uint64_t)acc, s));
+        work = own->p;
     }
     // A: for every residue j0 (mod n2) an n1-point DFT over j1 of x[j1*n2 + j0], times
     //    exp(-2 pi i j0 k1 / n), stored at scratch[k1*n2 + j0]

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""BASELINE config 3: np.fft.fftn of a complex64 1024^3 volume on 1/2/4/8 GPUs.
+"""Exchange-engine comparison for BASELINE config 3 (np.fft.fftn of a complex64 1024^3 volume on 1/2/4/8 GPUs): --exchange
+fused / symm / nccl.  (The driver-visible number, with parity against the reference, is the `fftn` object of bench.py's JSON
+line; this script only compares the three engines -- profiles/r01_fftn_*gpu_*.json.)
 
 N=1: one c2c(axes=[0,1,2]) call on the resident volume.  N>1 (torchrun, one rank per GPU):
 slab decomposition (rocket_fft_b200.distributed.SlabFFTN): local planes -> pack -> NCCL
@@ -7,9 +9,9 @@ all-to-all over NVLink -> axis-0 lines.  Strong scaling (total work fixed).  Pri
 line: total ms (CUDA events, max over ranks), the all-to-all alone, and its bus bandwidth
 = bytes sent per GPU / time (same definition as nccl-tests' alltoall busbw).
 
-    python bench_fftn.py --steps 5
+    python tools/bench_fftn_engines.py --steps 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        --master-port 29511 bench_fftn.py --steps 5
+        --master-port 29511 tools/bench_fftn_engines.py --steps 5
 """
 import argparse
 import json
@@ -17,7 +19,7 @@ import math
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
